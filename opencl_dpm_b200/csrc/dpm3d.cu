@@ -1,0 +1,468 @@
+// dpm3d.cu — C ABI of the 3D path: handle, topology tables, upload / step / download.
+// Host-side counterpart of src/Tissue3D.cpp:199-470 in the reference (buffers, kernel
+// arguments, the step loop and the two read-backs), over CUDA instead of OpenCL.
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "dpm3d_kernels.cuh"
+
+using namespace dpm;
+
+struct dpm3d_ctx {
+  int device = 0;
+  int nc = 0, nv = 0, nf = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  float4 *pos[2] = {nullptr, nullptr};
+  float4 *force = nullptr;
+  float4 *bnd[2] = {nullptr, nullptr};
+  float4 *cellA = nullptr, *cellB = nullptr;
+  ushort4 *faces = nullptr;
+  uint16_t *ring_nbr = nullptr, *ring_face = nullptr;
+  uint8_t *valence = nullptr;
+  int ring_stride = 0;
+  // neighbour search
+  NbrState *st = nullptr;
+  float4 *bbox_lo = nullptr, *bbox_hi = nullptr;
+  int *bin_id = nullptr, *order = nullptr, *bin_count = nullptr, *bin_start = nullptr, *cand_count = nullptr, *cand = nullptr;
+  float *partial = nullptr;
+  int *chunk_sum = nullptr;
+  int cap = 0, K = 32, K_alloc = 0;
+  float skin_rel = 0.1f;
+  int coop_grid = 0;
+  int cur = 0;
+  unsigned mask = DPM3D_ALL;
+  bool uploaded = false;
+  int threads = 0, vpt = 0;
+  size_t smem = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float4 *h_cell = nullptr;  // pinned staging for per-cell parameters
+  dpm_stats_t stats{};
+  int last_pbc = -1;
+  float last_L = -1.f;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Ring adjacency of a closed oriented 2-manifold: for vertex v the cyclic list n_0..n_{k-1}
+// such that ring face i is (v, n_i, n_{i+1}) in the mesh orientation.
+int build_rings(int nv, int nf, const uint32_t *faces, std::vector<uint16_t> &ring_nbr, std::vector<uint16_t> &ring_face,
+                std::vector<uint8_t> &valence, int &stride) {
+  std::vector<std::vector<std::array<uint32_t, 3>>> inc(nv);  // (next, nextnext, face)
+  for (int f = 0; f < nf; f++) {
+    for (int k = 0; k < 3; k++) {
+      uint32_t v = faces[3 * f + k], a = faces[3 * f + (k + 1) % 3], b = faces[3 * f + (k + 2) % 3];
+      if (v >= (uint32_t)nv || a >= (uint32_t)nv || b >= (uint32_t)nv)
+        return fail(DPM_ERR_RUNTIME, "Invalid face indices");  // src/Tissue3D.cpp:149-154
+      if (v == a || a == b || v == b) return fail(DPM_ERR_TOPOLOGY, "degenerate face (repeated vertex index)");
+      inc[v].push_back({a, b, (uint32_t)f});
+    }
+  }
+  int maxval = 0;
+  for (int v = 0; v < nv; v++) maxval = std::max(maxval, (int)inc[v].size());
+  if (maxval > 16) return fail(DPM_ERR_TOPOLOGY, "vertex valence > 16 is not supported");
+  stride = maxval;
+  ring_nbr.assign((size_t)nv * stride, 0);
+  ring_face.assign((size_t)nv * stride, 0);
+  valence.assign(nv, 0);
+  for (int v = 0; v < nv; v++) {
+    auto &L = inc[v];
+    int k = (int)L.size();
+    if (k < 3) return fail(DPM_ERR_TOPOLOGY, "mesh is not closed: a vertex has fewer than 3 incident faces");
+    std::vector<char> used(k, 0);
+    uint32_t cur = 0;  // start at the lowest-index incident face (inc lists are in face order)
+    for (int i = 0; i < k; i++) {
+      if (used[cur]) return fail(DPM_ERR_TOPOLOGY, "vertex fan is not a single cycle (non-manifold mesh)");
+      used[cur] = 1;
+      ring_nbr[(size_t)v * stride + i] = (uint16_t)L[cur][0];
+      ring_face[(size_t)v * stride + i] = (uint16_t)L[cur][2];
+      uint32_t want = L[cur][1];
+      int nxt = -1;
+      for (int q = 0; q < k; q++)
+        if (L[q][0] == want) { if (nxt >= 0) return fail(DPM_ERR_TOPOLOGY, "edge shared by more than two faces"); nxt = q; }
+      if (nxt < 0) return fail(DPM_ERR_TOPOLOGY, "mesh is not closed or not consistently oriented");
+      cur = (uint32_t)nxt;
+    }
+    if (cur != 0) return fail(DPM_ERR_TOPOLOGY, "vertex fan does not close");
+    valence[v] = (uint8_t)k;
+  }
+  return DPM_OK;
+}
+
+template <int T, int V>
+cudaError_t launch_step_t(const Step3DParams &p, size_t smem, cudaStream_t s) {
+  dpm3d_step_kernel<T, V><<<p.nc, T, smem, s>>>(p);
+  return cudaGetLastError();
+}
+template <int T, int V>
+cudaError_t set_smem_t(size_t smem) {
+  return cudaFuncSetAttribute(dpm3d_step_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+int pick_config(dpm3d_ctx *h) {
+  const int nv = h->nv;
+  if (nv <= 192) { h->threads = 192; h->vpt = 1; }
+  else if (nv <= 1024) { h->threads = 256; h->vpt = (nv + 255) / 256; }
+  else return fail(DPM_ERR_INVALID_ARGUMENT, "meshes with more than 1024 vertices per cell are not supported yet");
+  return DPM_OK;
+}
+
+size_t smem_for(dpm3d_ctx *h) {
+  return h->threads == 192 ? step3d_smem_bytes<192>(h->nv, h->nf, h->K) : step3d_smem_bytes<256>(h->nv, h->nf, h->K);
+}
+
+cudaError_t set_smem(dpm3d_ctx *h) {
+  if (h->threads == 192) return set_smem_t<192, 1>(h->smem);
+  switch (h->vpt) {
+    case 1: return set_smem_t<256, 1>(h->smem);
+    case 2: return set_smem_t<256, 2>(h->smem);
+    case 3: return set_smem_t<256, 3>(h->smem);
+    default: return set_smem_t<256, 4>(h->smem);
+  }
+}
+
+cudaError_t launch_step(dpm3d_ctx *h, const Step3DParams &p) {
+  if (h->threads == 192) return launch_step_t<192, 1>(p, h->smem, h->stream);
+  switch (h->vpt) {
+    case 1: return launch_step_t<256, 1>(p, h->smem, h->stream);
+    case 2: return launch_step_t<256, 2>(p, h->smem, h->stream);
+    case 3: return launch_step_t<256, 3>(p, h->smem, h->stream);
+    default: return launch_step_t<256, 4>(p, h->smem, h->stream);
+  }
+}
+
+NbrBuffers nbr_buffers(dpm3d_ctx *h, int pbc, float L) {
+  NbrBuffers nb{};
+  nb.st = h->st;
+  nb.blo = h->bnd[h->cur];
+  nb.bhi = h->bnd[h->cur] + 1;
+  nb.blo_stride = 3;
+  nb.bbox_lo = h->bbox_lo; nb.bbox_hi = h->bbox_hi;
+  nb.bin_id = h->bin_id; nb.order = h->order; nb.bin_count = h->bin_count; nb.bin_start = h->bin_start;
+  nb.cand_count = h->cand_count; nb.cand = h->cand;
+  nb.partial = h->partial; nb.chunk_sum = h->chunk_sum;
+  nb.nc = h->nc; nb.nc_list = h->nc; nb.nd = 3; nb.cap = h->cap; nb.K = h->K;
+  nb.pbc = pbc; nb.L = L; nb.skin_rel = h->skin_rel; nb.range = 0.0f; nb.far2d = 0;
+  nb.range_from_bounds = 1; nb.range_scale = RANGE_HEADROOM;
+  return nb;
+}
+
+int alloc_cand(dpm3d_ctx *h) {
+  if (h->K_alloc >= h->K) return DPM_OK;
+  if (h->cand) cudaFree(h->cand);
+  h->cand = nullptr;
+  DPM_CUDA_TRY(cudaMalloc(&h->cand, sizeof(int) * (size_t)h->nc * h->K));
+  h->K_alloc = h->K;
+  return DPM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dpm3d_create(dpm3d_t **out, int device, int ncells, int nv, int nf, const uint32_t *faces) {
+  if (!out) return fail(DPM_ERR_INVALID_ARGUMENT, "handle pointer is NULL");
+  *out = nullptr;
+  if (ncells <= 0) return fail(DPM_ERR_INVALID_ARGUMENT, "NCELLS must be positive");  // src/Tissue3D.cpp:132-135
+  if (nv < 4 || nf < 4 || !faces) return fail(DPM_ERR_INVALID_ARGUMENT, "bad mesh size");
+  int ndev = 0;
+  DPM_CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(DPM_ERR_CUDA, "no such CUDA device (there is no CPU fallback)");
+  std::vector<uint16_t> rn, rf;
+  std::vector<uint8_t> val;
+  int stride = 0;
+  int rc = build_rings(nv, nf, faces, rn, rf, val, stride);
+  if (rc) return rc;
+  DeviceGuard guard(device);
+  dpm3d_ctx *h = new dpm3d_ctx();
+  h->device = device; h->nc = ncells; h->nv = nv; h->nf = nf; h->ring_stride = stride;
+  rc = pick_config(h);
+  if (rc) { delete h; return rc; }
+  auto bail = [&](int code) { dpm3d_destroy(h); return code; };
+#define TRYB(expr)                                                                                    \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess) return bail(fail(DPM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e))); \
+  } while (0)
+  TRYB(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  TRYB(cudaEventCreate(&h->ev0));
+  TRYB(cudaEventCreate(&h->ev1));
+  const size_t nvert = (size_t)ncells * nv;
+  TRYB(cudaMalloc(&h->pos[0], sizeof(float4) * nvert));
+  TRYB(cudaMalloc(&h->pos[1], sizeof(float4) * nvert));
+  TRYB(cudaMalloc(&h->force, sizeof(float4) * nvert));
+  TRYB(cudaMemsetAsync(h->force, 0, sizeof(float4) * nvert, h->stream));
+  TRYB(cudaMalloc(&h->bnd[0], sizeof(float4) * 3 * ncells));
+  TRYB(cudaMalloc(&h->bnd[1], sizeof(float4) * 3 * ncells));
+  TRYB(cudaMalloc(&h->cellA, sizeof(float4) * ncells));
+  TRYB(cudaMalloc(&h->cellB, sizeof(float4) * ncells));
+  TRYB(cudaMallocHost(&h->h_cell, sizeof(float4) * 2 * ncells));
+  TRYB(cudaMalloc(&h->faces, sizeof(ushort4) * nf));
+  TRYB(cudaMalloc(&h->ring_nbr, sizeof(uint16_t) * rn.size()));
+  TRYB(cudaMalloc(&h->ring_face, sizeof(uint16_t) * rf.size()));
+  TRYB(cudaMalloc(&h->valence, nv));
+  {
+    std::vector<ushort4> f4(nf);
+    for (int f = 0; f < nf; f++) f4[f] = make_ushort4((unsigned short)faces[3 * f], (unsigned short)faces[3 * f + 1], (unsigned short)faces[3 * f + 2], 0);
+    TRYB(cudaMemcpy(h->faces, f4.data(), sizeof(ushort4) * nf, cudaMemcpyHostToDevice));
+    TRYB(cudaMemcpy(h->ring_nbr, rn.data(), sizeof(uint16_t) * rn.size(), cudaMemcpyHostToDevice));
+    TRYB(cudaMemcpy(h->ring_face, rf.data(), sizeof(uint16_t) * rf.size(), cudaMemcpyHostToDevice));
+    TRYB(cudaMemcpy(h->valence, val.data(), nv, cudaMemcpyHostToDevice));
+  }
+  h->cap = 4 * ncells + 1024;
+  TRYB(cudaMalloc(&h->st, sizeof(NbrState)));
+  TRYB(cudaMemset(h->st, 0, sizeof(NbrState)));
+  TRYB(cudaMalloc(&h->bbox_lo, sizeof(float4) * ncells));
+  TRYB(cudaMalloc(&h->bbox_hi, sizeof(float4) * ncells));
+  TRYB(cudaMalloc(&h->bin_id, sizeof(int) * ncells));
+  TRYB(cudaMalloc(&h->order, sizeof(int) * ncells));
+  TRYB(cudaMalloc(&h->bin_count, sizeof(int) * (h->cap + 1)));
+  TRYB(cudaMalloc(&h->bin_start, sizeof(int) * (h->cap + 1)));
+  TRYB(cudaMalloc(&h->cand_count, sizeof(int) * ncells));
+  h->coop_grid = rebuild_max_grid(device);
+  TRYB(cudaMalloc(&h->partial, sizeof(float) * 16 * h->coop_grid));
+  TRYB(cudaMalloc(&h->chunk_sum, sizeof(int) * h->coop_grid));
+  rc = alloc_cand(h);
+  if (rc) return bail(rc);
+  h->smem = smem_for(h);
+  TRYB(set_smem(h));
+#undef TRYB
+  *out = h;
+  return DPM_OK;
+}
+
+int dpm3d_destroy(dpm3d_t *h) {
+  if (!h) return DPM_OK;
+  DeviceGuard guard(h->device);
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  void *ptrs[] = {h->pos[0], h->pos[1], h->force, h->bnd[0], h->bnd[1], h->cellA, h->cellB, h->faces, h->ring_nbr, h->ring_face,
+                  h->valence, h->st, h->bbox_lo, h->bbox_hi, h->bin_id, h->order, h->bin_count, h->bin_start, h->cand_count,
+                  h->cand, h->partial, h->chunk_sum};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  if (h->h_cell) cudaFreeHost(h->h_cell);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return DPM_OK;
+}
+
+int dpm3d_set_stream(dpm3d_t *h, void *cuda_stream) {
+  if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return DPM_OK;
+}
+
+int dpm3d_set_neighbor_params(dpm3d_t *h, float skin_rel, int max_candidates) {
+  if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
+  if (!(skin_rel >= 0.0f) || max_candidates < 1 || max_candidates > 128)
+    return fail(DPM_ERR_INVALID_ARGUMENT, "skin_rel must be >= 0 and 1 <= max_candidates <= 128");
+  DeviceGuard guard(h->device);
+  h->skin_rel = skin_rel;
+  h->K = max_candidates;
+  int rc = alloc_cand(h);
+  if (rc) return rc;
+  h->smem = smem_for(h);
+  DPM_CUDA_TRY(set_smem(h));
+  h->uploaded = false;  // lists must be rebuilt: require a fresh upload
+  return DPM_OK;
+}
+
+int dpm3d_set_force_mask(dpm3d_t *h, unsigned mask) {
+  if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
+  h->mask = mask & DPM3D_ALL;
+  return DPM_OK;
+}
+
+static int upload_common(dpm3d_t *h, const float *verts4, bool on_device, const float *Kv, const float *Ka, const float *Ks,
+                         const float *v0, const float *a0, const float *l0) {
+  if (!h || !verts4 || !Kv || !Ka || !Ks || !v0 || !a0 || !l0) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL argument");
+  DeviceGuard guard(h->device);
+  for (int c = 0; c < h->nc; c++) {
+    h->h_cell[c] = make_float4(Kv[c], Ka[c], Ks[c], v0[c]);
+    h->h_cell[h->nc + c] = make_float4(a0[c], l0[c], 0.f, 0.f);
+  }
+  h->cur = 0;
+  const size_t bytes = sizeof(float4) * (size_t)h->nc * h->nv;
+  DPM_CUDA_TRY(cudaMemcpyAsync(h->pos[0], verts4, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  DPM_CUDA_TRY(cudaMemcpyAsync(h->cellA, h->h_cell, sizeof(float4) * h->nc, cudaMemcpyHostToDevice, h->stream));
+  DPM_CUDA_TRY(cudaMemcpyAsync(h->cellB, h->h_cell + h->nc, sizeof(float4) * h->nc, cudaMemcpyHostToDevice, h->stream));
+  DPM_CUDA_TRY(cudaMemsetAsync(h->st, 0, sizeof(NbrState), h->stream));
+  dpm3d_bounds_kernel<<<h->nc, 128, sizeof(float4) * h->nv, h->stream>>>(h->pos[0], h->bnd[0], h->nc, h->nv, h->ring_nbr,
+                                                                          h->valence, h->ring_stride);
+  DPM_CUDA_TRY(cudaGetLastError());
+  h->stats.launches += 1;
+  // mark the neighbour lists stale
+  static const int one = 1;
+  DPM_CUDA_TRY(cudaMemcpyAsync(&h->st->rebuild, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  // the pinned parameter staging buffer is reused by the next upload: wait for the copies
+  DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->uploaded = true;
+  return DPM_OK;
+}
+
+int dpm3d_upload(dpm3d_t *h, const float *verts4, const float *Kv, const float *Ka, const float *Ks, const float *v0,
+                 const float *a0, const float *l0) {
+  return upload_common(h, verts4, false, Kv, Ka, Ks, v0, a0, l0);
+}
+int dpm3d_upload_device(dpm3d_t *h, const float *verts4_dev, const float *Kv, const float *Ka, const float *Ks,
+                        const float *v0, const float *a0, const float *l0) {
+  return upload_common(h, verts4_dev, true, Kv, Ka, Ks, v0, a0, l0);
+}
+
+int dpm3d_rebuild_neighbors(dpm3d_t *h, int pbc, float L) {
+  if (!h || !h->uploaded) return fail(DPM_ERR_INVALID_ARGUMENT, "upload first");
+  DeviceGuard guard(h->device);
+  static const int one = 1;
+  DPM_CUDA_TRY(cudaMemcpyAsync(&h->st->rebuild, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  DPM_CUDA_TRY(launch_rebuild(nbr_buffers(h, pbc, L), h->stream, h->coop_grid));
+  h->stats.launches += 1;
+  h->last_pbc = pbc; h->last_L = L;
+  return DPM_OK;
+}
+
+int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, float L) {
+  (void)Kat;  // AllVertAttraction is never enqueued by the reference host
+  if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
+  if (nsteps <= 0) return fail(DPM_ERR_INVALID_ARGUMENT, "nsteps must be positive");                          // src/Tissue3D.cpp:123-126
+  if (!(dt > 0.0f) || dt > 0.1f) return fail(DPM_ERR_INVALID_ARGUMENT, "dt must be positive and reasonable");  // :127-131
+  if (!h->uploaded) return fail(DPM_ERR_INVALID_ARGUMENT, "dpm3d_step before dpm3d_upload");
+  DeviceGuard guard(h->device);
+  Step3DParams p{};
+  p.cellA = h->cellA; p.cellB = h->cellB; p.faces = h->faces;
+  p.ring_nbr = h->ring_nbr; p.ring_face = h->ring_face; p.valence = h->valence; p.ring_stride = h->ring_stride;
+  p.cand_count = h->cand_count; p.cand = h->cand; p.K = h->K;
+  p.bbox_lo = h->bbox_lo; p.bbox_hi = h->bbox_hi; p.st = h->st;
+  p.nc = h->nc; p.nv = h->nv; p.nf = h->nf; p.dt = dt; p.Kc = Kre; p.pbc = pbc; p.L = L; p.mask = h->mask;
+  if (pbc != h->last_pbc || L != h->last_L) {  // the lists depend on the box: rebuild when the caller changed it
+    static const int one = 1;
+    DPM_CUDA_TRY(cudaMemcpyAsync(&h->st->rebuild, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    h->last_pbc = pbc; h->last_L = L;
+  }
+  for (int s = 0; s < nsteps; s++) {
+    DPM_CUDA_TRY(launch_rebuild(nbr_buffers(h, pbc, L), h->stream, h->coop_grid));
+    p.pos_in = h->pos[h->cur]; p.pos_out = h->pos[h->cur ^ 1];
+    p.bnd_in = h->bnd[h->cur]; p.bnd_out = h->bnd[h->cur ^ 1];
+    p.force_out = (s == nsteps - 1) ? h->force : nullptr;  // forces are only read back after the last step (:425-434)
+    DPM_CUDA_TRY(launch_step(h, p));
+    h->cur ^= 1;
+  }
+  h->stats.steps += (uint64_t)nsteps;
+  h->stats.launches += 2ull * (uint64_t)nsteps;
+  return DPM_OK;
+}
+
+static int check_device_flags(dpm3d_t *h) {
+  NbrState st;
+  DPM_CUDA_TRY(cudaMemcpyAsync(&st, h->st, sizeof(NbrState), cudaMemcpyDeviceToHost, h->stream));
+  DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->stats.rebuilds = (uint64_t)st.nbuilds;
+  h->stats.contact_evals = st.contact_evals;
+  if (st.overflow) return fail(DPM_ERR_RUNTIME, "neighbour candidate list overflow: raise max_candidates (dpm3d_set_neighbor_params)");
+  return DPM_OK;
+}
+
+int dpm3d_sync(dpm3d_t *h) {
+  if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
+  DeviceGuard guard(h->device);
+  return check_device_flags(h);
+}
+
+int dpm3d_download(dpm3d_t *h, float *verts4, float *forces4) {
+  if (!h || !h->uploaded) return fail(DPM_ERR_INVALID_ARGUMENT, "nothing to download");
+  DeviceGuard guard(h->device);
+  const size_t bytes = sizeof(float4) * (size_t)h->nc * h->nv;
+  if (verts4) DPM_CUDA_TRY(cudaMemcpyAsync(verts4, h->pos[h->cur], bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (forces4) DPM_CUDA_TRY(cudaMemcpyAsync(forces4, h->force, bytes, cudaMemcpyDeviceToHost, h->stream));
+  return check_device_flags(h);
+}
+
+int dpm3d_device_state(dpm3d_t *h, float **verts4_dev, float **forces4_dev) {
+  if (!h || !h->uploaded) return fail(DPM_ERR_INVALID_ARGUMENT, "no device state");
+  if (verts4_dev) *verts4_dev = reinterpret_cast<float *>(h->pos[h->cur]);
+  if (forces4_dev) *forces4_dev = reinterpret_cast<float *>(h->force);
+  return DPM_OK;
+}
+
+int dpm3d_euler_update(dpm3d_t *h, float *verts4, float *forces4, const float *Kv, const float *Ka, const float *Ks,
+                       const float *v0, const float *a0, const float *l0, int nsteps, float dt, float Kre, float Kat, int pbc,
+                       float L, float *loop_ms) {
+  if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
+  if (nsteps <= 0) return fail(DPM_ERR_INVALID_ARGUMENT, "nsteps must be positive");
+  if (!(dt > 0.0f) || dt > 0.1f) return fail(DPM_ERR_INVALID_ARGUMENT, "dt must be positive and reasonable");
+  DeviceGuard guard(h->device);
+  for (int attempt = 0;; attempt++) {
+    int rc = dpm3d_upload(h, verts4, Kv, Ka, Ks, v0, a0, l0);
+    if (rc) return rc;
+    DPM_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    rc = dpm3d_step(h, nsteps, dt, Kre, Kat, pbc, L);
+    if (rc) return rc;
+    DPM_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    rc = check_device_flags(h);
+    if (rc == DPM_ERR_RUNTIME && h->K < 128 && attempt < 3) {  // candidate overflow: grow K and redo from the host state
+      int rc2 = dpm3d_set_neighbor_params(h, h->skin_rel, std::min(128, h->K * 2));
+      if (rc2) return rc2;
+      continue;
+    }
+    if (rc) return rc;
+    break;
+  }
+  if (loop_ms) DPM_CUDA_TRY(cudaEventElapsedTime(loop_ms, h->ev0, h->ev1));
+  return dpm3d_download(h, verts4, forces4);
+}
+
+int dpm3d_get_neighbor_artifacts(dpm3d_t *h, dpm_grid_t *grid, int32_t *bin_id, int32_t *order, int32_t *bin_start,
+                                 int32_t *cand_count, int32_t *cand) {
+  if (!h || !h->uploaded) return fail(DPM_ERR_INVALID_ARGUMENT, "no neighbour state");
+  DeviceGuard guard(h->device);
+  DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  NbrState st;
+  DPM_CUDA_TRY(cudaMemcpy(&st, h->st, sizeof(NbrState), cudaMemcpyDeviceToHost));
+  if (grid) *grid = st.grid;
+  if (bin_id) DPM_CUDA_TRY(cudaMemcpy(bin_id, h->bin_id, sizeof(int) * h->nc, cudaMemcpyDeviceToHost));
+  if (order) DPM_CUDA_TRY(cudaMemcpy(order, h->order, sizeof(int) * h->nc, cudaMemcpyDeviceToHost));
+  if (bin_start) DPM_CUDA_TRY(cudaMemcpy(bin_start, h->bin_start, sizeof(int) * (st.grid.nbins + 1), cudaMemcpyDeviceToHost));
+  if (cand_count) DPM_CUDA_TRY(cudaMemcpy(cand_count, h->cand_count, sizeof(int) * h->nc, cudaMemcpyDeviceToHost));
+  if (cand) DPM_CUDA_TRY(cudaMemcpy(cand, h->cand, sizeof(int) * (size_t)h->nc * h->K, cudaMemcpyDeviceToHost));
+  return DPM_OK;
+}
+
+int dpm3d_get_cell_bounds(dpm3d_t *h, float *bounds12) {
+  if (!h || !h->uploaded || !bounds12) return fail(DPM_ERR_INVALID_ARGUMENT, "no state");
+  DeviceGuard guard(h->device);
+  DPM_CUDA_TRY(cudaMemcpyAsync(bounds12, h->bnd[h->cur], sizeof(float4) * 3 * h->nc, cudaMemcpyDeviceToHost, h->stream));
+  DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return DPM_OK;
+}
+
+int dpm3d_get_stats(dpm3d_t *h, dpm_stats_t *out) {
+  if (!h || !out) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out = h->stats;
+  return DPM_OK;
+}
+int dpm3d_reset_stats(dpm3d_t *h) {
+  if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
+  memset(&h->stats, 0, sizeof(h->stats));
+  return DPM_OK;
+}
+
+int dpm_nccl_unique_id(uint8_t id[128]) {
+  (void)id;
+  return fail(DPM_ERR_NCCL, "multi-GPU path not built in this revision");
+}
+int dpm3d_shard_init(dpm3d_t *h, int rank, int nranks, const uint8_t id[128], int max_ghost) {
+  (void)h; (void)rank; (void)nranks; (void)id; (void)max_ghost;
+  return fail(DPM_ERR_NCCL, "multi-GPU path not built in this revision");
+}
+
+}  // extern "C"

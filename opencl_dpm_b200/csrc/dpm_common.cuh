@@ -1,0 +1,98 @@
+// dpm_common.cuh — shared device/host helpers for the B200 DPM hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/dpm_b200.h"
+
+namespace dpm {
+
+// ---- error plumbing (no exceptions across the C ABI) ------------------------
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+
+#define DPM_CUDA_TRY(expr)                                                                       \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return ::dpm::fail(DPM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+  } while (0)
+
+// ---- neighbour-search state kept on the device ------------------------------
+struct NbrState {
+  dpm_grid_t grid;
+  int rebuild;   // lists are stale: rebuild before the next step
+  int overflow;  // a candidate list exceeded K
+  int nbuilds;
+  int pad;
+  unsigned long long contact_evals;
+  // global raw (unwrapped) extent, for the 2D |d|>L partner search
+  float glo[3];
+  float ghi[3];
+  float range;  // interaction range the current lists were built for (3D: 1.16 * max edge bound * headroom)
+  float pad1;
+};
+
+// Cell-list buffers (all device pointers)
+struct NbrBuffers {
+  NbrState *st;
+  const float4 *blo;  // per cell: (lo.xyz, *)  exact AABB of current positions
+  const float4 *bhi;  // per cell: (hi.xyz, *)
+  int blo_stride;     // float4 stride between cells in blo/bhi arrays
+  float4 *bbox_lo;    // AABB at build time, grown by skin/2
+  float4 *bbox_hi;
+  int *bin_id;
+  int *order;
+  int *bin_count;  // cap+1, doubles as scatter fill counter
+  int *bin_start;  // cap+1
+  int *cand_count;
+  int *cand;
+  float *partial;  // [grid][16] block partials of the reduction
+  int *chunk_sum;  // [grid]
+  int nc;          // cells binned (owned + ghosts)
+  int nc_list;     // cells that get candidate lists (owned)
+  int nd;
+  int cap;
+  int K;
+  int pbc;
+  float L;
+  float skin_rel;
+  float range;        // explicit interaction range (range_from_bounds == 0)
+  int range_from_bounds;  // 1: range = range_scale * max_c bhi[c].w (per-cell contact pad), recorded in st->range
+  float range_scale;
+  int far2d;
+};
+
+// Launches the cooperative rebuild kernel (no-op on the device when st->rebuild == 0).
+cudaError_t launch_rebuild(const NbrBuffers &nb, cudaStream_t stream, int coop_grid);
+int rebuild_max_grid(int device);
+
+// ---- small device helpers -----------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// x - L*roundf(x/L) with every operation individually rounded (bit-exact with the CPU spec)
+__device__ __forceinline__ float minimg_rn(float d, float L) {
+  return __fsub_rn(d, __fmul_rn(L, roundf(__fdiv_rn(d, L))));
+}
+__device__ __forceinline__ float wrap_rn(float c, int pbc, float L) {
+  return pbc ? __fsub_rn(c, __fmul_rn(L, floorf(__fdiv_rn(c, L)))) : c;
+}
+#endif
+
+}  // namespace dpm

@@ -1,0 +1,56 @@
+// Tissue.hpp — DPM::Tissue3D / DPM::Tissue2D with the public surface of the reference's
+// include/Tissue.hpp:13-55.  The four cl:: members of each class (platform, device,
+// program, context) are replaced by one opaque device handle over the C ABI in
+// include/dpm_b200.h; everything a caller can name is unchanged.
+#ifndef DPM_B200_TISSUE_HPP
+#define DPM_B200_TISSUE_HPP
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "cell.hpp"
+
+namespace DPM {
+
+struct DeviceHandle3D;  // owns a dpm3d_t*
+struct DeviceHandle2D;  // owns a dpm2d_t*
+
+class Tissue3D {
+public:
+  int NCELLS;
+  int PBC;  // (boolean) periodic boundary conditions
+  float L;
+  float Kre;
+  float Kat;
+  std::string attractionMethod;
+  std::vector<DPM::Cell3D> Cells;
+
+  Tissue3D(std::vector<DPM::Cell3D> cells, float phi0);
+
+  void CLEulerUpdate(int nsteps, float dt);
+  void Disperse2D();
+
+private:
+  std::shared_ptr<DeviceHandle3D> dev;  // created on first use; copies of a Tissue share it
+};
+
+class Tissue2D {
+public:
+  std::vector<Cell2D> cells;
+  int NCELLS;
+  bool PBC;
+  float Kre;
+  float Kat;
+  float phi0;
+  float L;
+  Tissue2D(std::vector<DPM::Cell2D> cells, float phi0);
+  void Disperse();
+  void CLEulerUpdate(int nsteps, float dt);
+
+private:
+  int maxNV;
+  std::shared_ptr<DeviceHandle2D> dev;
+};
+
+}  // namespace DPM
+#endif

@@ -1,0 +1,173 @@
+// Tissue3D.cpp — host side of the 3D hot path over the C ABI.
+//
+// Mirrors DPM::Tissue3D of the reference (src/Tissue3D.cpp): same constructor arithmetic
+// (:16-29), same Disperse2D behaviour (:40-116), and a CLEulerUpdate with the same
+// validation, exceptions, stdout/stderr messages and post-conditions (:118-522) — but the
+// OpenCL program build, the ten cl::Buffers, six cl::Kernels and the per-step enqueue loop
+// (:199-470) are ONE call into dpm3d_euler_update (include/dpm_b200.h).
+#include <cmath>
+#include <iostream>
+#include <stdexcept>
+
+#include "Tissue.hpp"
+#include "disperse.hpp"
+#include "dpm_b200.h"
+
+namespace DPM {
+
+struct DeviceHandle3D {
+  dpm3d_t *h = nullptr;
+  int ncells = 0;
+  std::vector<uint32_t> faces;
+  ~DeviceHandle3D() {
+    if (h) dpm3d_destroy(h);
+  }
+};
+
+static std::string last_error() {
+  char buf[1024];
+  dpm_last_error(buf, sizeof buf);
+  return std::string(buf);
+}
+
+Tissue3D::Tissue3D(std::vector<DPM::Cell3D> cells, float phi0) {
+  Cells = cells;
+  NCELLS = Cells.size();
+  if (NCELLS > 100) {
+    // kept for output fidelity (reference :19-23); the all-pairs limit behind it is gone
+    std::cerr << "Warning: Large number of cells, too many cells may crash program!" << std::endl;
+  }
+  float volume = 0.0f;
+  for (int ci = 0; ci < NCELLS; ci++) volume += Cells[ci].v0;
+  L = cbrt(volume) / phi0;
+  PBC = true;
+  Kre = 0.0f;  // uninitialised in the reference; callers always set it
+  Kat = 0.0f;
+  attractionMethod.assign("General");
+}
+
+void Tissue3D::Disperse2D() {
+  std::vector<float> radius(NCELLS), X, Y;
+  for (int i = 0; i < NCELLS; i++) radius[i] = Cells[i].r0 * 2;
+  if (detail::relax_centres(radius, L, X, Y))
+    std::cerr << "Warning: Max timesteps for dispersion reached" << std::endl;
+  // reference :106-115 — the centre is SUBTRACTED (sic), z is left untouched
+  for (int i = 0; i < NCELLS; i++) {
+    std::array<float, 3> com = Cells[i].GetCOM();
+    for (unsigned int j = 0; j < Cells[i].NV; j++) {
+      Cells[i].Verts[j][0] -= com[0];
+      Cells[i].Verts[j][1] -= com[1];
+      Cells[i].Verts[j][0] -= X[i];
+      Cells[i].Verts[j][1] -= Y[i];
+    }
+  }
+}
+
+void Tissue3D::CLEulerUpdate(int nsteps, float dt) {
+  const int NF = Cell3D::NF;
+  const int NV = Cell3D::NV;
+
+  // ---- argument validation: same conditions, messages and exception types as reference :123-135
+  if (nsteps <= 0) {
+    std::cerr << "[ERROR] Invalid nsteps: " << nsteps << std::endl;
+    throw std::invalid_argument("nsteps must be positive");
+  }
+  if (dt <= 0.0f || dt > 0.1f) {
+    std::cerr << "[ERROR] Invalid dt: " << dt << " (should be in range (0, 0.1])" << std::endl;
+    throw std::invalid_argument("dt must be positive and reasonable");
+  }
+  if (NCELLS <= 0) {
+    std::cerr << "[ERROR] Invalid NCELLS: " << NCELLS << std::endl;
+    throw std::invalid_argument("NCELLS must be positive");
+  }
+
+  // ---- pack: topology from Cells[0] only (:144-155), per-cell scalars and float4 vertices (:157-197)
+  std::vector<uint32_t> faces(3 * NF);
+  for (int fi = 0; fi < NF; fi++) {
+    const auto &f = Cells[0].Faces[fi];
+    if (f[0] >= (unsigned)NV || f[1] >= (unsigned)NV || f[2] >= (unsigned)NV) {
+      std::cerr << "[ERROR] Invalid face index at face " << fi << ": (" << f[0] << "," << f[1] << "," << f[2] << ")"
+                << std::endl;
+      throw std::runtime_error("Invalid face indices");
+    }
+    faces[3 * fi] = f[0]; faces[3 * fi + 1] = f[1]; faces[3 * fi + 2] = f[2];
+  }
+  std::vector<float> verts((size_t)NCELLS * NV * 4, 0.0f), forces((size_t)NCELLS * NV * 4, 0.0f);
+  std::vector<float> Kv(NCELLS), Ka(NCELLS), Ks(NCELLS), v0(NCELLS), a0(NCELLS), l0(NCELLS);
+  for (int ci = 0; ci < NCELLS; ci++) {
+    const Cell3D &c = Cells[ci];
+    if (c.Kv <= 0 || c.Ka <= 0 || c.Ks <= 0) {
+      std::cerr << "[ERROR] Invalid spring constants for cell " << ci << ": Kv=" << c.Kv << ", Ka=" << c.Ka
+                << ", Ks=" << c.Ks << std::endl;
+      throw std::runtime_error("Invalid spring constants");
+    }
+    if (c.v0 <= 0 || c.a0 <= 0) {
+      std::cerr << "[ERROR] Invalid reference values for cell " << ci << ": v0=" << c.v0 << ", a0=" << c.a0 << std::endl;
+      throw std::runtime_error("Invalid reference values");
+    }
+    Kv[ci] = c.Kv; Ka[ci] = c.Ka; Ks[ci] = c.Ks; v0[ci] = c.v0; a0[ci] = c.a0;
+    l0[ci] = sqrt(4.0f * c.a0) / sqrt(3.0f);  // rest edge length of an equilateral triangle of area a0 (:177)
+    for (int vi = 0; vi < NV; vi++) {
+      float *dst = &verts[((size_t)ci * NV + vi) * 4];
+      for (int d = 0; d < 3; d++) {
+        if (!std::isfinite(c.Verts[vi][d])) {
+          std::cerr << "[ERROR] Non-finite vertex coordinate at cell " << ci << ", vertex " << vi << ", coord " << d
+                    << ": " << c.Verts[vi][d] << std::endl;
+          throw std::runtime_error("Non-finite vertex coordinates");
+        }
+        dst[d] = c.Verts[vi][d];
+      }
+    }
+  }
+
+  // ---- device: one handle per tissue, re-created only if the size or topology changed
+  try {
+    if (!dev) dev = std::make_shared<DeviceHandle3D>();
+    if (!dev->h || dev->ncells != NCELLS || dev->faces != faces) {
+      if (dev->h) { dpm3d_destroy(dev->h); dev->h = nullptr; }
+      if (dpm3d_create(&dev->h, 0, NCELLS, NV, NF, faces.data()) != DPM_OK) throw std::runtime_error(last_error());
+      dev->ncells = NCELLS;
+      dev->faces = faces;
+    }
+    float loop_ms = 0.0f;
+    const int rc = dpm3d_euler_update(dev->h, verts.data(), forces.data(), Kv.data(), Ka.data(), Ks.data(), v0.data(),
+                                      a0.data(), l0.data(), nsteps, dt, Kre, Kat, PBC, L, &loop_ms);
+    if (rc == DPM_ERR_INVALID_ARGUMENT) throw std::invalid_argument(last_error());
+    if (rc != DPM_OK) throw std::runtime_error(last_error());
+    // same two lines the reference prints after its step loop (:454-461); the time is the
+    // CUDA-event time of the step loop, rounded to whole milliseconds as the reference does
+    const long long ms = (long long)loop_ms;
+    std::cout << nsteps << " timesteps completed in " << ms << " ms" << std::endl;
+    std::cout << "Average time per step: " << (ms / static_cast<double>(nsteps)) << " ms" << std::endl;
+  } catch (const std::exception &e) {
+    std::cerr << "[ERROR] Exception caught: " << e.what() << std::endl;
+    throw;
+  }
+
+  // ---- unpack + checks (:477-521)
+  for (int ci = 0; ci < NCELLS; ci++) {
+    for (int vi = 0; vi < NV; vi++) {
+      const float *pv = &verts[((size_t)ci * NV + vi) * 4], *pf = &forces[((size_t)ci * NV + vi) * 4];
+      for (int d = 0; d < 3; d++) {
+        if (!std::isfinite(pv[d])) {
+          std::cerr << "[ERROR] Non-finite result vertex at cell " << ci << ", vertex " << vi << ", coord " << d << ": "
+                    << pv[d] << std::endl;
+          throw std::runtime_error("Non-finite simulation results");
+        }
+        if (!std::isfinite(pf[d]))
+          std::cerr << "[WARNING] Non-finite force at cell " << ci << ", vertex " << vi << ", coord " << d << ": " << pf[d]
+                    << std::endl;
+      }
+      Cells[ci].Verts[vi] = {pv[0], pv[1], pv[2]};
+      Cells[ci].Forces[vi] = {pf[0], pf[1], pf[2]};
+    }
+    Cells[ci].Volume = Cells[ci].GetVolume();
+    Cells[ci].SurfaceArea = Cells[ci].GetSurfaceArea();
+    if (!std::isfinite(Cells[ci].Volume) || Cells[ci].Volume <= 0)
+      std::cerr << "[WARNING] Invalid volume for cell " << ci << ": " << Cells[ci].Volume << std::endl;
+    if (!std::isfinite(Cells[ci].SurfaceArea) || Cells[ci].SurfaceArea <= 0)
+      std::cerr << "[WARNING] Invalid surface area for cell " << ci << ": " << Cells[ci].SurfaceArea << std::endl;
+  }
+}
+
+}  // namespace DPM

@@ -1,0 +1,57 @@
+// bindings.cpp — pybind11 module `clDPM`: the reference's Python surface
+// (src/DPMWrapper.cpp:11-17, src/CellWrapper.cpp:7-29, src/TissueWrapper.cpp:7-29),
+// bound to the B200 host classes.  Attribute names, read/write-ness and method names
+// are identical; T.Cells stays copy-on-access through the STL casters.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "Tissue.hpp"
+
+namespace py = pybind11;
+using namespace DPM;
+
+PYBIND11_MODULE(clDPM, m) {
+  m.doc() = "Deformable Particle Model — B200-native (CUDA sm_100a) drop-in for OpenCL_DPM's clDPM";
+
+  py::class_<Cell2D>(m, "Cell2D")
+      .def(py::init<float, float, float, unsigned int, float>())
+      .def_readwrite("Ka", &Cell2D::Ka)
+      .def_readwrite("Kl", &Cell2D::Kl)
+      .def_readwrite("Kb", &Cell2D::Kb)
+      .def_readwrite("Verts", &Cell2D::Verticies)
+      .def_readwrite("Forces", &Cell2D::Forces);
+
+  py::class_<Tissue2D>(m, "Tissue2D")
+      .def(py::init<std::vector<Cell2D>, float>())
+      .def_readwrite("Cells", &Tissue2D::cells)
+      .def_readonly("NCELLS", &Tissue2D::NCELLS)
+      .def_readonly("L", &Tissue2D::L)
+      .def_readonly("PBC", &Tissue2D::PBC)
+      .def_readwrite("Kre", &Tissue2D::Kre)
+      .def_readwrite("Kat", &Tissue2D::Kat)
+      .def("CLEulerUpdate", &Tissue2D::CLEulerUpdate)
+      .def("Disperse", &Tissue2D::Disperse);
+
+  py::class_<Cell3D>(m, "Cell3D")
+      .def(py::init<std::array<float, 3>, float, float>())
+      .def_readwrite("Kv", &Cell3D::Kv)
+      .def_readwrite("Ka", &Cell3D::Ka)
+      .def_readwrite("Ks", &Cell3D::Ks)
+      .def_readwrite("Verts", &Cell3D::Verts)
+      .def("GetVolume", &Cell3D::GetVolume)
+      .def("GetPositions", &Cell3D::GetPositions)
+      .def("GetVesselPositions", &Cell3D::GetVesselPositions)
+      .def("GetFaces", &Cell3D::GetFaces)
+      .def("GetForces", &Cell3D::GetForces);
+
+  py::class_<Tissue3D>(m, "Tissue3D")
+      .def(py::init<std::vector<Cell3D>, float>())
+      .def_readwrite("Kre", &Tissue3D::Kre)
+      .def_readwrite("Kat", &Tissue3D::Kat)
+      .def_readwrite("Cells", &Tissue3D::Cells)
+      .def_readonly("NCELLS", &Tissue3D::NCELLS)
+      .def_readonly("L", &Tissue3D::L)
+      .def_readonly("PBC", &Tissue3D::PBC)
+      .def("CLEulerUpdate", &Tissue3D::CLEulerUpdate)
+      .def("Disperse2D", &Tissue3D::Disperse2D);
+}

@@ -1,0 +1,186 @@
+"""TEST INFRASTRUCTURE — ctypes wrapper of oracle/liboracle_dpm.so (the CPU restatement of the
+reference kernels).  Never imported by the product package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboracle_dpm.so")
+
+_lib = None
+
+
+def build(force: bool = False) -> None:
+    srcs = [os.path.join(HERE, f) for f in ("dpm_oracle.c", "dpm_oracle_impl.h", "Makefile")]
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
+        subprocess.check_call(["make", "-C", HERE, "liboracle_dpm.so"], stdout=subprocess.DEVNULL)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+    return _lib
+
+
+class Grid(C.Structure):
+    _fields_ = [("nb", C.c_int32 * 3), ("periodic", C.c_int32 * 3), ("allpass", C.c_int32 * 3),
+                ("origin", C.c_float * 3), ("inv_binw", C.c_float * 3), ("max_ext", C.c_float),
+                ("margin", C.c_float), ("nbins", C.c_int32), ("pad", C.c_int32)]
+
+    def as_tuple(self):
+        return (tuple(self.nb), tuple(self.periodic), tuple(self.allpass), tuple(self.origin),
+                tuple(self.inv_binw), self.max_ext, self.margin, self.nbins)
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def _real(dtype):
+    return (C.c_float, "_f32") if dtype == np.float32 else (C.c_double, "_f64")
+
+
+def _arr(x, n, dtype):
+    return np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype), (n,)), dtype=dtype)
+
+
+# ---------------------------------------------------------------- 3D
+def forces3d(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, which=15, cand_count=None, cand=None,
+             dtype=np.float32, want_contacts=False):
+    """Forces of one step from positions verts4 [(nc*nv),4]. Returns forces [(nc*nv),4] (and contacts)."""
+    ct, sfx = _real(dtype)
+    faces = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+    nf = faces.shape[0]
+    nc = len(np.atleast_1d(np.asarray(v0))) if np.ndim(v0) else None
+    V = np.ascontiguousarray(verts4, dtype=dtype).reshape(-1, 4)
+    if nc is None:
+        raise ValueError("per-cell arrays required")
+    nv = V.shape[0] // nc
+    Fo = np.zeros_like(V)
+    P = [_arr(x, nc, dtype) for x in (Kv, Ka, Ks, v0, a0, l0)]
+    contacts = np.zeros((nc * nv, 2), np.int32) if want_contacts else None
+    K = 0 if cand is None else cand.shape[1]
+    fn = getattr(lib(), "oracle3d_forces" + sfx)
+    fn.restype = None
+    fn(nc, nv, nf, _p(faces, C.c_uint32), _p(V, ct), _p(Fo, ct), *[_p(x, ct) for x in P], ct(Kc), int(PBC), ct(L),
+       int(which), _p(None if cand_count is None else np.ascontiguousarray(cand_count, np.int32), C.c_int32),
+       _p(None if cand is None else np.ascontiguousarray(cand, np.int32), C.c_int32), int(K), _p(contacts, C.c_int32))
+    return (Fo, contacts) if want_contacts else Fo
+
+
+def run3d(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, nsteps, dt, which=15, dtype=np.float32):
+    """nsteps of the all-pairs reference algorithm. Returns (verts4, last_forces4)."""
+    ct, sfx = _real(dtype)
+    faces = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+    nf = faces.shape[0]
+    nc = len(np.asarray(v0))
+    V = np.array(verts4, dtype=dtype, copy=True).reshape(-1, 4)
+    nv = V.shape[0] // nc
+    Fo = np.zeros_like(V)
+    P = [_arr(x, nc, dtype) for x in (Kv, Ka, Ks, v0, a0, l0)]
+    fn = getattr(lib(), "oracle3d_run" + sfx)
+    fn.restype = None
+    fn(nc, nv, nf, _p(faces, C.c_uint32), _p(V, ct), _p(Fo, ct), *[_p(x, ct) for x in P], ct(Kc), int(PBC), ct(L),
+       int(nsteps), ct(dt), int(which))
+    return V, Fo
+
+
+def aabb3d(verts4, nc):
+    V = np.ascontiguousarray(verts4, np.float32).reshape(-1, 4)
+    nv = V.shape[0] // nc
+    lo = np.zeros((nc, 3), np.float32); hi = np.zeros((nc, 3), np.float32)
+    lib().oracle_aabb3d(nc, nv, _p(V, C.c_float), _p(lo, C.c_float), _p(hi, C.c_float))
+    return lo, hi
+
+
+# ---------------------------------------------------------------- 2D
+def forces2d(verts2, NV, Ka, Kl, Kb, a0, l0, r0, Kre, Kat, PBC, L, which=31, cand_count=None, cand=None,
+             dtype=np.float32, want_inside=False):
+    ct, sfx = _real(dtype)
+    V = np.ascontiguousarray(verts2, dtype=dtype)
+    nc, S = V.shape[0], V.shape[1]
+    NV = _arr(NV, nc, np.int32)
+    Fo = np.zeros_like(V)
+    P = [_arr(x, nc, dtype) for x in (Ka, Kl, Kb, a0, l0, r0)]
+    inside = np.zeros((nc, S), np.int32) if want_inside else None
+    K = 0 if cand is None else cand.shape[1]
+    fn = getattr(lib(), "oracle2d_forces" + sfx)
+    fn.restype = None
+    fn(nc, S, _p(NV, C.c_int32), _p(V, ct), _p(Fo, ct), *[_p(x, ct) for x in P], ct(Kre), ct(Kat), int(PBC), ct(L),
+       int(which), _p(None if cand_count is None else np.ascontiguousarray(cand_count, np.int32), C.c_int32),
+       _p(None if cand is None else np.ascontiguousarray(cand, np.int32), C.c_int32), int(K), _p(inside, C.c_int32))
+    return (Fo, inside) if want_inside else Fo
+
+
+def run2d(verts2, NV, Ka, Kl, Kb, a0, l0, r0, Kre, Kat, PBC, L, nsteps, dt, which=31, dtype=np.float32):
+    ct, sfx = _real(dtype)
+    V = np.array(verts2, dtype=dtype, copy=True)
+    nc, S = V.shape[0], V.shape[1]
+    NV = _arr(NV, nc, np.int32)
+    Fo = np.zeros_like(V)
+    P = [_arr(x, nc, dtype) for x in (Ka, Kl, Kb, a0, l0, r0)]
+    fn = getattr(lib(), "oracle2d_run" + sfx)
+    fn.restype = None
+    fn(nc, S, _p(NV, C.c_int32), _p(V, ct), _p(Fo, ct), *[_p(x, ct) for x in P], ct(Kre), ct(Kat), int(PBC), ct(L),
+       int(nsteps), ct(dt), int(which))
+    return V, Fo
+
+
+def aabb2d(verts2, NV):
+    V = np.ascontiguousarray(verts2, np.float32)
+    nc, S = V.shape[0], V.shape[1]
+    NV = _arr(NV, nc, np.int32)
+    lo = np.zeros((nc, 3), np.float32); hi = np.zeros((nc, 3), np.float32)
+    lib().oracle_aabb2d(nc, S, _p(NV, C.c_int32), _p(V, C.c_float), _p(lo, C.c_float), _p(hi, C.c_float))
+    return lo, hi
+
+
+# ---------------------------------------------------------------- cell list spec
+def cell_list(nd, lo, hi, PBC, L, skin_rel, rng, K, cap=None, far2d=False):
+    lo = np.ascontiguousarray(lo, np.float32); hi = np.ascontiguousarray(hi, np.float32)
+    nc = lo.shape[0]
+    cap = 4 * nc + 1024 if cap is None else cap
+    g = Grid()
+    bin_id = np.zeros(nc, np.int32); order = np.zeros(nc, np.int32); bin_start = np.zeros(cap + 1, np.int32)
+    cc = np.zeros(nc, np.int32); cand = np.zeros((nc, K), np.int32)
+    lib().oracle_cell_list(int(nd), nc, _p(lo, C.c_float), _p(hi, C.c_float), int(PBC), C.c_float(L), C.c_float(skin_rel),
+                           C.c_float(rng), int(cap), int(K), int(far2d), C.byref(g), _p(bin_id, C.c_int32),
+                           _p(order, C.c_int32), _p(bin_start, C.c_int32), _p(cc, C.c_int32), _p(cand, C.c_int32))
+    return dict(grid=g, bin_id=bin_id, order=order, bin_start=bin_start[:g.nbins + 1].copy(), cand_count=cc, cand=cand)
+
+
+# ---------------------------------------------------------------- geometry
+def icosphere(subdiv=2):
+    nv, nf = 10 * 4 ** subdiv + 2, 20 * 4 ** subdiv
+    V = np.zeros((nv, 3), np.float32); F = np.zeros((nf, 3), np.uint32)
+    lib().oracle_icosphere.restype = C.c_int
+    n = lib().oracle_icosphere(int(subdiv), _p(V, C.c_float), _p(F, C.c_uint32))
+    assert n == nv
+    return V, F
+
+
+def cell3d_params(calA, r0, nf):
+    out = np.zeros(4, np.float32)
+    lib().oracle_cell3d_params(C.c_float(calA), C.c_float(r0), int(nf), _p(out, C.c_float))
+    return dict(v0=out[0], sa0=out[1], a0=out[2], l0=out[3])
+
+
+def cell3d_place(unitV, r0, start):
+    unitV = np.ascontiguousarray(unitV, np.float32)
+    nv = unitV.shape[0]
+    out = np.zeros((nv, 4), np.float32)
+    st = np.asarray(start, np.float32)
+    lib().oracle_cell3d_place(nv, _p(unitV, C.c_float), C.c_float(r0), _p(st, C.c_float), _p(out, C.c_float))
+    return out
+
+
+def cell2d_init(x0, y0, calA, NV, r0):
+    verts = np.zeros((NV, 2), np.float32); out = np.zeros(3, np.float32)
+    lib().oracle_cell2d_init(C.c_float(x0), C.c_float(y0), C.c_float(calA), int(NV), C.c_float(r0), _p(verts, C.c_float), _p(out, C.c_float))
+    return verts, dict(calA0=out[0], a0=out[1], l0=out[2])

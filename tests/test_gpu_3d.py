@@ -1,0 +1,209 @@
+"""GPU parity tests for the 3D hot path (run on the B200 box: pytest -m gpu).
+
+Every compute call goes through the C ABI (libdpm_b200.so via ctypes); the CPU oracle
+(oracle/) is only the checker.  Tolerances follow SURVEY.md §8(c):
+  integer artefacts bit-exact; forces/positions per step within
+  1e-5 * max(|F_ref|_inf over the tissue, 1e-3).
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+PKEYS = ("Kv", "Ka", "Ks", "v0", "a0", "l0")
+
+
+def _oracle():
+    from oracle import oracle as O
+
+    return O
+
+
+def _handle(d, **kw):
+    from opencl_dpm_b200 import Dpm3D
+
+    h = Dpm3D(d["nc"], d["nv"], d["faces"])
+    if kw:
+        h.set_neighbor_params(**kw)
+    return h
+
+
+def _gpu_step(h, d, verts, nsteps=1, mask=15):
+    h.set_force_mask(mask)
+    h.upload(verts, *[d[k] for k in PKEYS])
+    h.step(nsteps, float(d["dt"]), float(d["Kre"]), 0.0, d["PBC"], float(d["L"]))
+    return h.download()
+
+
+@pytest.mark.parametrize("cfg", ["test3d_py", "test3d_cpp"])
+@pytest.mark.parametrize("mask", [1, 2, 4, 8, 15])
+def test_single_step_force_parity(cfg, mask):
+    """One step from the reference demo's initial state: forces and positions vs the all-pairs oracle."""
+    O = _oracle()
+    d = H.config_test3d_py(64) if cfg == "test3d_py" else H.config_test3d_cpp()
+    h = _handle(d)
+    V1, F = _gpu_step(h, d, d["verts"], 1, mask)
+    Fref = O.forces3d(d["verts"], d["faces"], *[d[k] for k in PKEYS], d["Kre"], d["PBC"], d["L"], which=mask)
+    tol = H.force_tol(Fref)
+    err = np.abs(F[:, :3] - Fref[:, :3]).max()
+    assert err <= tol, f"force error {err:.3e} > {tol:.3e} (|F|max {np.abs(Fref).max():.3f})"
+    Vref = d["verts"].copy()
+    Vref[:, :3] += Fref[:, :3] * d["dt"]
+    assert np.abs(V1[:, :3] - Vref[:, :3]).max() <= tol * float(d["dt"]) + 4e-7 * np.abs(Vref).max()
+    h.close()
+
+
+def test_multi_step_parity_each_step_from_oracle_state():
+    """20 steps; before every step the GPU is re-seeded with the oracle's state, so each step is an
+    independent parity check on an evolving configuration (contacts appear and disappear)."""
+    O = _oracle()
+    d = H.config_test3d_py(64)
+    h = _handle(d)
+    V = d["verts"].copy()
+    worst = 0.0
+    for s in range(20):
+        V1, F = _gpu_step(h, d, V)
+        Fref = O.forces3d(V, d["faces"], *[d[k] for k in PKEYS], d["Kre"], d["PBC"], d["L"])
+        worst = max(worst, np.abs(F[:, :3] - Fref[:, :3]).max() / H.force_tol(Fref))
+        V[:, :3] += Fref[:, :3] * d["dt"]
+    assert worst <= 1.0, f"worst per-step force error is {worst:.2f}x the tolerance"
+    h.close()
+
+
+def test_trajectory_100_steps_vs_oracle():
+    """reference test3D.cpp verbatim: 30 cells, 100 steps, dt 0.005 — final positions vs the fp32 all-pairs
+    oracle, with the fp32-vs-fp64 oracle drift reported alongside (chaos vs arithmetic)."""
+    O = _oracle()
+    d = H.config_test3d_cpp()
+    h = _handle(d)
+    V1, F1 = _gpu_step(h, d, d["verts"], 100)
+    Vr, Fr = O.run3d(d["verts"], d["faces"], *[d[k] for k in PKEYS], d["Kre"], d["PBC"], d["L"], 100, d["dt"])
+    V64, _ = O.run3d(d["verts"], d["faces"], *[d[k] for k in PKEYS], d["Kre"], d["PBC"], d["L"], 100, d["dt"], dtype=np.float64)
+    scale = np.abs(Vr[:, :3]).max()
+    gpu_vs_f32 = np.abs(V1[:, :3] - Vr[:, :3]).max() / scale
+    f32_vs_f64 = np.abs(Vr[:, :3] - V64[:, :3]).max() / scale
+    print(f"drift over 100 steps: gpu-vs-f32 {gpu_vs_f32:.3e}  f32-vs-f64 {f32_vs_f64:.3e}")
+    # stated trajectory tolerance: 1e-4 relative over 100 steps, and never worse than 20x the oracle's own fp32 drift
+    assert gpu_vs_f32 <= max(1e-4, 20 * f32_vs_f64)
+    assert np.abs(F1[:, :3] - Fr[:, :3]).max() <= 50 * H.force_tol(Fr)
+    h.close()
+
+
+def test_com_and_volume_are_bit_exact():
+    """The two ill-conditioned per-cell sums are evaluated in the reference's serial order with
+    individually rounded ops: COM and signed volume must equal the oracle's bit for bit."""
+    O = _oracle()
+    d = H.config_test3d_cpp()
+    h = _handle(d)
+    _gpu_step(h, d, d["verts"], 1)
+    b = h.cell_bounds()  # bounds of the NEW positions; volume of the step's START positions
+    V0 = d["verts"].reshape(d["nc"], d["nv"], 4)
+    faces = d["faces"]
+    for ci in range(d["nc"]):
+        vol = np.float32(0)
+        for f in faces:
+            P0, P1, P2 = V0[ci, f[0], :3], V0[ci, f[1], :3], V0[ci, f[2], :3]
+            c = np.array([P0[1] * P1[2] - P0[2] * P1[1], P0[2] * P1[0] - P0[0] * P1[2], P0[0] * P1[1] - P0[1] * P1[0]], np.float32)
+            t = np.float32(np.float32(np.float32(c[0] * P2[0]) + np.float32(c[1] * P2[1])) + np.float32(c[2] * P2[2]))
+            vol = np.float32(vol + np.float32(t / np.float32(6.0)))
+        assert np.float32(abs(vol)).tobytes() == b[ci, 11].tobytes(), (ci, vol, b[ci, 11])
+    V1, _ = h.download()
+    V1 = V1.reshape(d["nc"], d["nv"], 4)
+    for ci in range(d["nc"]):
+        s = np.zeros(3, np.float32)
+        for i in range(d["nv"]):
+            s = (s + V1[ci, i, :3]).astype(np.float32)
+        com = (s * np.float32(np.float32(1.0) / np.float32(d["nv"]))).astype(np.float32)
+        assert com.tobytes() == b[ci, 8:11].tobytes(), (ci, com, b[ci, 8:11])
+    lo, hi = O.aabb3d(V1.reshape(-1, 4), d["nc"])
+    assert lo.tobytes() == b[:, 0:3].astype(np.float32).tobytes()
+    assert hi.tobytes() == b[:, 4:7].astype(np.float32).tobytes()
+    h.close()
+
+
+@pytest.mark.parametrize("cfg", ["test3d_py", "test3d_cpp", "nonperiodic"])
+def test_neighbor_artifacts_bit_exact(cfg):
+    """Cell-list artefacts (grid, bin ids, sorted permutation, bin starts, candidate lists) vs the CPU spec."""
+    O = _oracle()
+    d = H.config_test3d_py(64) if cfg != "test3d_cpp" else H.config_test3d_cpp()
+    pbc = 0 if cfg == "nonperiodic" else 1
+    h = _handle(d)
+    h.upload(d["verts"], *[d[k] for k in PKEYS])
+    h.rebuild_neighbors(pbc, float(d["L"]))
+    art = h.neighbor_artifacts()
+    b = h.cell_bounds()
+    lo, hi = O.aabb3d(d["verts"], d["nc"])
+    assert lo.tobytes() == np.ascontiguousarray(b[:, 0:3]).tobytes() and hi.tobytes() == np.ascontiguousarray(b[:, 4:7]).tobytes()
+    rng = np.float32(1.25) * b[:, 7].max()  # RANGE_HEADROOM * largest contact pad, as the device computes it
+    ref = O.cell_list(3, lo, hi, pbc, d["L"], 0.1, rng, h.K)
+    assert art["grid"].as_tuple() == ref["grid"].as_tuple()
+    for k in ("bin_id", "order", "bin_start", "cand_count"):
+        assert np.array_equal(art[k], ref[k]), k
+    for i in range(d["nc"]):
+        n = ref["cand_count"][i]
+        assert np.array_equal(art["cand"][i, :n], ref["cand"][i, :n]), i
+    h.close()
+
+
+def test_contact_set_matches_all_pairs():
+    """{(vertex): number of force-carrying contacts} from the culled GPU path == all-pairs oracle, via the
+    repulsion-only force: a vertex has nonzero repulsion iff the oracle has a contact there."""
+    O = _oracle()
+    d = H.config_test3d_py(64)
+    h = _handle(d)
+    _, F = _gpu_step(h, d, d["verts"], 1, mask=8)
+    Fref, con = O.forces3d(d["verts"], d["faces"], *[d[k] for k in PKEYS], d["Kre"], d["PBC"], d["L"], which=8, want_contacts=True)
+    gpu_has = np.abs(F[:, :3]).max(1) > 1e-3 * 0.5 * float(d["Kre"]) * 0.999
+    ref_has = con[:, 0] > 0
+    assert con[:, 0].sum() > 100, "config has too few contacts to be a meaningful test"
+    assert np.array_equal(gpu_has, ref_has), f"{(gpu_has != ref_has).sum()} vertices differ"
+    print(f"force-carrying contacts {con[:, 0].sum()}, noise-level contacts {con[:, 1].sum()}")
+    h.close()
+
+
+def test_euler_update_one_call_and_rebuilds():
+    """dpm3d_euler_update (the CLEulerUpdate seam): host buffers in/out equals upload+step+download, and
+    a long run triggers neighbour rebuilds without changing results vs a run with a huge skin."""
+    d = H.config_test3d_cpp()
+    h = _handle(d)
+    V = d["verts"].copy()
+    F = np.zeros_like(V)
+    ms = h.euler_update(V, *[d[k] for k in PKEYS], 200, float(d["dt"]), float(d["Kre"]), 0.0, d["PBC"], float(d["L"]), forces_out=F)
+    assert ms > 0
+    V1, F1 = _gpu_step(h, d, d["verts"], 200)
+    assert np.array_equal(V, V1) and np.array_equal(F, F1)
+    st = h.stats()
+    h2 = _handle(d, skin_rel=0.02, max_candidates=32)
+    V2, F2 = _gpu_step(h2, d, d["verts"], 200)
+    st2 = h2.stats()
+    print(f"rebuilds: skin 0.1 -> {st.rebuilds}, skin 0.02 -> {st2.rebuilds}")
+    assert st2.rebuilds > st.rebuilds >= 1
+    assert np.array_equal(V1, V2) and np.array_equal(F1, F2), "results must not depend on the skin / rebuild schedule"
+    h.close(); h2.close()
+
+
+def test_errors_and_validation():
+    from opencl_dpm_b200 import Dpm3D, DpmError
+
+    d = H.config_test3d_cpp()
+    h = _handle(d)
+    with pytest.raises(DpmError) as e:
+        h.step(1, 0.005, 1.0)
+    assert e.value.code == 1  # step before upload
+    h.upload(d["verts"], *[d[k] for k in PKEYS])
+    for bad in [dict(nsteps=0, dt=0.005), dict(nsteps=1, dt=0.0), dict(nsteps=1, dt=0.2)]:
+        with pytest.raises(DpmError) as e:
+            h.step(bad["nsteps"], bad["dt"], 1.0)
+        assert e.value.code == 1
+    bad_faces = d["faces"].copy()
+    bad_faces[0, 0] = 9999
+    with pytest.raises(DpmError) as e:
+        Dpm3D(2, 162, bad_faces)
+    assert e.value.code == 2 and "Invalid face indices" in str(e.value)
+    open_faces = d["faces"][:-1]
+    with pytest.raises(DpmError) as e:
+        Dpm3D(2, 162, open_faces)
+    assert e.value.code == 4
+    h.close()
