@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native OpenCL_DPM hot path.
+
+Metric (BASELINE.json): vertex-steps/s of the fused force+integrate step, plus the fraction
+of the HBM roofline at 32 B (3D) / 16 B (2D) algorithmic bytes per vertex-step.
+
+A bench "step" = one CLEulerUpdate-equivalent pass over the tissue: `--inner` timesteps of
+{forces, Euler}.  `value` is measured with inputs resident in HBM (CUDA events on the stream
+the kernels are launched on, around dpm3d_step only — what the reference's own timer brackets,
+src/Tissue3D.cpp:369,454).  `e2e` is the same metric through the reference-facing one-call
+seam dpm3d_euler_update with PINNED HOST buffers: H2D of the vertices and per-cell parameters,
+the step loop, D2H of vertices and last-step forces, wall-clock.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload D642|D162|C162|B2D] [--inner T]
+  python bench.py --impl reference ...   # the reference algorithm on the host cores (oracle arm)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PK3 = ("Kv", "Ka", "Ks", "v0", "a0", "l0")
+PK2 = ("Ka", "Kl", "Kb", "a0", "l0", "r0")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_workload(name: str, rank: int = 0):
+    from opencl_dpm_b200 import synth
+
+    if name == "D642":
+        d = synth.monolayer3d(64, subdiv=3)
+        desc = "3D DPM 4096-cell monolayer, 642-vertex icospheres (2,629,632 vertices), winding-number repulsion, substrate, PBC"
+    elif name == "D162":
+        d = synth.monolayer3d(64, subdiv=2)
+        desc = "3D DPM 4096-cell monolayer, 162-vertex icospheres (663,552 vertices; the reference's mesh)"
+    elif name == "C162":
+        d = synth.monolayer3d(8, subdiv=2)
+        desc = "3D DPM 64-cell monolayer, 162-vertex icospheres"
+    elif name == "B2D":
+        d = synth.tissue2d(64, nv=64)
+        desc = "2D DPM 4096 cells x 64 vertices, area+perimeter+bending+attraction+repulsion, PBC"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    d["name"], d["desc"], d["dim"] = name, desc, (2 if name == "B2D" else 3)
+    return d
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks/throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_baseline_sample(d, budget_s: float = 20.0):
+    """The reference's ALL-PAIRS algorithm (oracle port, fp32, OpenMP over cells) on a bounded sample of
+    the same workload: forces for the first `ncells_sample` cells against all cells, one timestep."""
+    from oracle import oracle as O
+
+    cores = os.cpu_count() or 1
+    if d["dim"] == 3:
+        # all-pairs cost per sampled cell: nv * (nc-1) * nf face evaluations, ~1.4e8 face-evals/s on 8 cores
+        per_cell = d["nv"] * (d["nc"] - 1) * d["nf"] / (1.8e7 * cores)
+        ns = int(max(1, min(d["nc"], budget_s / max(per_cell, 1e-9))))
+        ns = min(ns, max(1, cores) * max(1, ns // max(1, cores)) if ns >= cores else ns)
+        t0 = time.perf_counter()
+        O.forces3d_range(d["verts"], d["faces"], *[d[k] for k in PK3], d["Kre"], d["PBC"], d["L"], 0, ns)
+        dt = time.perf_counter() - t0
+        nvert = ns * d["nv"]
+        sample = f"all-pairs forces of the first {ns} of {d['nc']} cells against all cells, 1 timestep ({dt:.1f} s)"
+    else:
+        ns = d["nc"]
+        t0 = time.perf_counter()
+        O.forces2d(d["verts"], d["nv"], *[d[k] for k in PK2], d["Kre"], d["Kat"], d["PBC"], d["L"])
+        dt = time.perf_counter() - t0
+        nvert = int(d["nv"].sum())
+        sample = f"all-pairs forces of all {ns} cells, 1 timestep ({dt:.1f} s)"
+    return {"value": nvert / dt, "unit": "vertex-steps/s", "cores": cores, "kind": "port", "sample": sample}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d = make_workload(args.workload)
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline_sample(d, budget_s=max(4.0, 40.0 / max(1, args.steps + args.warmup)))
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = float(np.mean(vals))
+    cb["value"] = v
+    out = {"impl": "reference", "metric": "vertex-steps/sec (force+integrate)", "value": v, "unit": "vertex-steps/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": {"workload": d["desc"], "name": d["name"], "algorithm": "reference all-pairs (CPU port of the OpenCL kernels)"},
+           "cpu_baseline": cb, "e2e": {"value": v, "unit": "vertex-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="D642")
+    ap.add_argument("--inner", type=int, default=20, help="timesteps per bench step (one CLEulerUpdate call)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+
+    from opencl_dpm_b200 import Dpm2D, Dpm3D, capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    capi.lib()
+    d = make_workload(args.workload, rank)
+    dim = d["dim"]
+    stream = torch.cuda.current_stream()
+    nvert = d["nc"] * d["nv"] if dim == 3 else int(d["nv"].sum())
+    balg = 32 if dim == 3 else 16
+
+    if dim == 3:
+        h = Dpm3D(d["nc"], d["nv"], d["faces"], device=local)
+        h.set_stream(stream.cuda_stream)
+        params = [d[k] for k in PK3]
+        dev_verts = torch.from_numpy(d["verts"]).cuda()
+
+        def reset():
+            h.upload_device(dev_verts.data_ptr(), *params)
+
+        def run_steps(n):
+            h.step(n, float(d["dt"]), float(d["Kre"]), 0.0, d["PBC"], float(d["L"]))
+        host_v = torch.from_numpy(d["verts"].copy()).pin_memory()
+        host_f = torch.zeros_like(host_v).pin_memory()
+        h2d = d["verts"].nbytes + 6 * 4 * d["nc"]
+        d2h = 2 * d["verts"].nbytes
+
+        def e2e_call(n):
+            host_v.copy_(torch.from_numpy(d["verts"]))
+            t0 = time.perf_counter()
+            h.euler_update(host_v.numpy(), *params, n, float(d["dt"]), float(d["Kre"]), 0.0, d["PBC"], float(d["L"]), forces_out=host_f.numpy())
+            return time.perf_counter() - t0
+    else:
+        h = Dpm2D(d["nc"], d["S"], device=local)
+        h.set_stream(stream.cuda_stream)
+        params = [d[k] for k in PK2]
+
+        def reset():
+            h.upload(d["verts"], d["nv"], *params)
+
+        def run_steps(n):
+            h.step(n, float(d["dt"]), float(d["Kre"]), float(d["Kat"]), d["PBC"], float(d["L"]))
+        host_v = torch.from_numpy(d["verts"].copy()).pin_memory()
+        host_f = torch.zeros_like(host_v).pin_memory()
+        h2d = d["verts"].nbytes + (6 * 4 + 4) * d["nc"]
+        d2h = 2 * d["verts"].nbytes
+
+        def e2e_call(n):
+            host_v.copy_(torch.from_numpy(d["verts"]))
+            t0 = time.perf_counter()
+            h.euler_update(host_v.numpy(), d["nv"], *params, n, float(d["dt"]), float(d["Kre"]), float(d["Kat"]), d["PBC"], float(d["L"]),
+                           forces_out=host_f.numpy())
+            return time.perf_counter() - t0
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) -----------------------------------------------
+    reset()
+    for _ in range(args.warmup):
+        run_steps(args.inner)
+    torch.cuda.synchronize()
+    launches0 = h.stats().launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for a, b in evs:
+        flush.fill_(1)  # flush L2 between timed steps (outside the event pair)
+        a.record(stream)
+        run_steps(args.inner)
+        b.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    h.sync()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    launches = h.stats().launches - launches0
+    st = h.stats()
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    total_vs = nvert * args.inner * args.steps * world
+    value = total_vs / (ms * 1e-3)
+
+    # ---- end-to-end through the one-call seam with pinned host buffers (`e2e`) ---------------
+    for _ in range(min(2, args.warmup)):
+        e2e_call(args.inner)
+    barrier()
+    te = [e2e_call(args.inner) for _ in range(args.steps)]
+    barrier()
+    e2e_t = float(np.sum(te))
+    if world > 1:
+        t = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = float(t.item())
+    e2e_value = nvert * args.inner * args.steps * world / e2e_t
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        n_step_kernels = args.inner * args.steps
+        t_launch = ms * 1e-3 / n_step_kernels  # step-kernel launches dominate the region (the rebuild kernel is a no-op launch)
+        achieved = nvert * balg / t_launch / 1e9
+        out = {
+            "metric": "vertex-steps/sec (force+integrate)", "value": value, "unit": "vertex-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": d["desc"], "name": d["name"], "timesteps_per_step": args.inner, "dt": float(d["dt"]),
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one tissue per GPU)",
+                       "l2": "L2 flushed (256 MiB write) between timed steps; within a step consecutive timesteps reuse L2 as in the real loop",
+                       "ms_per_timestep": ms / n_step_kernels},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "vertex-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_t * 1e3 / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "dpm3d_step_kernel" if dim == 3 else "dpm2d_step_kernel", "achieved": achieved,
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_vertex_step": balg, "us_per_launch": t_launch * 1e6},
+            "stats": {"rebuilds": int(st.rebuilds), "contact_evals_per_timestep": st.contact_evals / max(1, st.steps),
+                      "wall_s_timed_region": t_wall},
+        }
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_sample(d)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -135,7 +135,9 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
     }
     const float lvx = pp1.x - p.x, lvy = pp1.y - p.y, lmx = p.x - pm1.x, lmy = p.y - pm1.y;
     if (P.mask & DPM2D_PERIMETER) {  // :109-118
-      const float len = sqrtf(lvx * lvx + lvy * lvy), lenm = sqrtf(lmx * lmx + lmy * lmy);
+      // edge strain len/l0 - 1 cancels to ~1e-2: keep the squared length unfused so it rounds like the reference's dot()
+      const float len = sqrtf(__fadd_rn(__fmul_rn(lvx, lvx), __fmul_rn(lvy, lvy)));
+      const float lenm = sqrtf(__fadd_rn(__fmul_rn(lmx, lmx), __fmul_rn(lmy, lmy)));
       const float dli = len / l0 - 1.0f, dlim1 = lenm / l0 - 1.0f;
       const float k = Kl * sqrtf(a0 / l0);
       fx += k * (dli * (lvx / len) - dlim1 * (lmx / lenm));
@@ -444,6 +446,7 @@ int dpm2d_upload(dpm2d_t *h, const float *verts2, const int32_t *nv, const float
   dpm2d_bounds_kernel<<<(h->nc + 3) / 4, 128, 0, h->stream>>>(h->pos[0], h->nv, h->bnd[0], h->nc, h->S);
   DPM_CUDA_TRY(cudaGetLastError());
   h->stats.launches += 1;
+  h->stats.steps = 0; h->stats.rebuilds = 0; h->stats.contact_evals = 0;
   int rc = mark_rebuild(h);
   if (rc) return rc;
   DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));

@@ -302,6 +302,7 @@ static int upload_common(dpm3d_t *h, const float *verts4, bool on_device, const 
                                                                           h->valence, h->ring_stride);
   DPM_CUDA_TRY(cudaGetLastError());
   h->stats.launches += 1;
+  h->stats.steps = 0; h->stats.rebuilds = 0; h->stats.contact_evals = 0;  // per-upload counters (launches stay cumulative)
   // mark the neighbour lists stale
   static const int one = 1;
   DPM_CUDA_TRY(cudaMemcpyAsync(&h->st->rebuild, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));

@@ -189,10 +189,10 @@ static inline REAL FN(repel_pair3d)(const REAL *Vj, const uint32_t *F, int nf, c
  * contacts (optional): per vertex, number of cells with |wn|>=1e-3 (force-carrying) and number
  * of noise-level contacts 1e-6<=|wn|<1e-3 are accumulated in contacts[2*vid+{0,1}].
  * Kernel order per step: src/Tissue3D.cpp:372-423. */
-void FN(oracle3d_forces)(int nc, int nv, int nf, const uint32_t *faces, const REAL *verts, REAL *forces,
-                         const REAL *Kv, const REAL *Ka, const REAL *Ks, const REAL *v0, const REAL *a0,
-                         const REAL *l0, REAL Kc, int PBC, REAL L, int which,
-                         const int32_t *cand_count, const int32_t *cand, int cand_stride, int32_t *contacts) {
+static void FN(forces3d_range)(int nc, int nv, int nf, const uint32_t *faces, const REAL *verts, REAL *forces,
+                               const REAL *Kv, const REAL *Ka, const REAL *Ks, const REAL *v0, const REAL *a0,
+                               const REAL *l0, REAL Kc, int PBC, REAL L, int which, const int32_t *cand_count,
+                               const int32_t *cand, int cand_stride, int32_t *contacts, int c0, int c1) {
   /* ClearForces :366-369 */
   memset(forces, 0, sizeof(REAL) * 4 * (size_t)nc * nv);
   REAL *coms = (REAL *)malloc(sizeof(REAL) * 3 * nc);
@@ -218,13 +218,14 @@ void FN(oracle3d_forces)(int nc, int nv, int nf, const uint32_t *faces, const RE
       if (x < lo[3 * ci + d]) lo[3 * ci + d] = x;
       if (x > hi[3 * ci + d]) hi[3 * ci + d] = x;
     }
+    if (ci < c0 || ci >= c1) continue; /* bounds/COM are needed for every cell, forces only for [c0,c1) */
     if (which & 1) FN(volume_force3d)(V, Fo, faces, nv, nf, Kv[ci], v0[ci]);
     if (which & 2) FN(area_force3d)(V, Fo, faces, nf, Ka[ci], a0[ci], l0[ci]);
     if (which & 4) FN(stick_force3d)(V, Fo, faces, nv, nf, Ks[ci], l0[ci]);
   }
   if ((which & 8) && Kc != (REAL)0.0) {
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int ci = 0; ci < nc; ci++) {
+    for (int ci = c0; ci < c1; ci++) {
       const REAL *comi = coms + 3 * ci;
       int ncand = cand ? cand_count[ci] : nc;
       for (int vi = 0; vi < nv; vi++) {
@@ -260,6 +261,23 @@ void FN(oracle3d_forces)(int nc, int nv, int nf, const uint32_t *faces, const RE
     }
   }
   free(coms); free(lo); free(hi); free(emax);
+}
+
+void FN(oracle3d_forces)(int nc, int nv, int nf, const uint32_t *faces, const REAL *verts, REAL *forces,
+                         const REAL *Kv, const REAL *Ka, const REAL *Ks, const REAL *v0, const REAL *a0,
+                         const REAL *l0, REAL Kc, int PBC, REAL L, int which,
+                         const int32_t *cand_count, const int32_t *cand, int cand_stride, int32_t *contacts) {
+  FN(forces3d_range)(nc, nv, nf, faces, verts, forces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, which, cand_count, cand,
+                     cand_stride, contacts, 0, nc);
+}
+
+/* Same, but forces are evaluated only for cells [c0, c1) (against ALL cells): a bounded sample of the
+ * reference's all-pairs work, used to time the CPU baseline on large tissues. */
+void FN(oracle3d_forces_range)(int nc, int nv, int nf, const uint32_t *faces, const REAL *verts, REAL *forces,
+                               const REAL *Kv, const REAL *Ka, const REAL *Ks, const REAL *v0, const REAL *a0,
+                               const REAL *l0, REAL Kc, int PBC, REAL L, int which, int c0, int c1) {
+  FN(forces3d_range)(nc, nv, nf, faces, verts, forces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, which, NULL, NULL, 0, NULL,
+                     c0, c1);
 }
 
 /* EulerPosition :371-381 */

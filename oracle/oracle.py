@@ -74,6 +74,21 @@ def forces3d(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, which=15, cand_c
     return (Fo, contacts) if want_contacts else Fo
 
 
+def forces3d_range(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, c0, c1, which=15):
+    """All-pairs forces (fp32) for cells [c0,c1) only — a bounded sample of the reference algorithm."""
+    faces = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+    nc = len(np.asarray(v0))
+    V = np.ascontiguousarray(verts4, dtype=np.float32).reshape(-1, 4)
+    nv = V.shape[0] // nc
+    Fo = np.zeros_like(V)
+    P = [_arr(x, nc, np.float32) for x in (Kv, Ka, Ks, v0, a0, l0)]
+    fn = lib().oracle3d_forces_range_f32
+    fn.restype = None
+    fn(nc, nv, faces.shape[0], _p(faces, C.c_uint32), _p(V, C.c_float), _p(Fo, C.c_float), *[_p(x, C.c_float) for x in P],
+       C.c_float(Kc), int(PBC), C.c_float(L), int(which), int(c0), int(c1))
+    return Fo
+
+
 def run3d(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, nsteps, dt, which=15, dtype=np.float32):
     """nsteps of the all-pairs reference algorithm. Returns (verts4, last_forces4)."""
     ct, sfx = _real(dtype)

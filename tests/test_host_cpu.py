@@ -1,0 +1,145 @@
+"""CPU tests (-m "not gpu"): the C ABI library loads and exports every symbol include/dpm_b200.h declares,
+and the host-side mirror of the reference interface (clDPM module) behaves like the reference's classes.
+No compute entry point is called without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers as H
+from conftest import ROOT, has_gpu
+
+
+def test_library_exports_every_declared_symbol():
+    from opencl_dpm_b200 import capi
+
+    hdr = open(os.path.join(ROOT, "include", "dpm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(dpm[23]?d?_\w+)\s*\(", hdr)))
+    assert len(names) >= 35, names
+    lib = capi.lib()
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared but not exported: {missing}"
+    assert b"sm_100a" in lib.dpm_version()
+
+
+def test_no_cpu_fallback_without_device():
+    from opencl_dpm_b200 import Dpm3D, DpmError, capi
+
+    if has_gpu():
+        pytest.skip("a GPU is present")
+    V, F = capi.icosphere(2)
+    with pytest.raises(DpmError) as e:
+        Dpm3D(2, 162, F)
+    assert e.value.code == 3  # DPM_ERR_CUDA: the product path fails loudly, it never computes on the CPU
+
+
+def test_abi_geometry_helpers_match_oracle_and_reference_constants():
+    from opencl_dpm_b200 import capi
+    from oracle import oracle as O
+
+    for s in (2, 3):
+        V, F = capi.icosphere(s)
+        Vo, Fo = O.icosphere(s)
+        assert np.array_equal(V, Vo) and np.array_equal(F, Fo)
+    p, po = capi.cell3d_params(1.05, 1.8, 320), O.cell3d_params(1.05, 1.8, 320)
+    assert all(p[k] == po[k] for k in p)
+
+
+def test_cldpm_surface_matches_reference_wrappers():
+    """names/readwrite-ness of src/CellWrapper.cpp:7-29 and src/TissueWrapper.cpp:7-29"""
+    m = H.cldpm()
+    c = m.Cell3D([0.0, 0.0, 0.0], 1.0, 1.0)
+    for a in ("Kv", "Ka", "Ks", "Verts"):
+        setattr(c, a, getattr(c, a))
+    for meth in ("GetVolume", "GetPositions", "GetVesselPositions", "GetFaces", "GetForces"):
+        assert callable(getattr(c, meth))
+    assert not hasattr(c, "Forces")  # 3D forces are only reachable through GetForces()
+    c2 = m.Cell2D(0.0, 0.0, 1.05, 32, 1.0)
+    for a in ("Ka", "Kl", "Kb", "Verts", "Forces"):
+        setattr(c2, a, getattr(c2, a))
+    T = m.Tissue3D([c] * 3, 0.35)
+    for a in ("Kre", "Kat", "Cells"):
+        setattr(T, a, getattr(T, a))
+    for a in ("NCELLS", "L", "PBC"):
+        getattr(T, a)
+        with pytest.raises(AttributeError):
+            setattr(T, a, 1)
+    assert callable(T.CLEulerUpdate) and callable(T.Disperse2D)
+    T2 = m.Tissue2D([c2] * 3, 0.85)
+    for a in ("Kre", "Kat", "Cells"):
+        setattr(T2, a, getattr(T2, a))
+    assert (T2.Kre, T2.Kat, T2.PBC) == (1.0, 0.0, True)
+    assert callable(T2.CLEulerUpdate) and callable(T2.Disperse)
+
+
+def test_cldpm_geometry_equals_reference_probe_values():
+    """values obtained by compiling the reference's own src/cell.cpp"""
+    m = H.cldpm()
+    c = m.Cell3D([0.0, 0.0, 0.0], 1.0, 1.0)
+    np.testing.assert_allclose(c.GetVolume(), 3.84748006, rtol=3e-7)
+    faces = np.asarray(c.GetFaces())
+    assert faces.shape == (320, 3) and tuple(faces[0]) == (0, 42, 44) and tuple(faces[319]) == (160, 161, 159)
+    np.testing.assert_allclose(np.asarray(c.Verts)[12], [-0.809017003, 0.44721356, 0.273520619], atol=1e-7)
+    pos = np.asarray(c.GetPositions())
+    assert pos.shape == (3, 162)
+    c = m.Cell3D([7.0, 6.0, 1.3], 1.05, 1.8)
+    np.testing.assert_allclose(c.GetVolume(), 22.4385052, rtol=3e-6)
+    T = m.Tissue3D([m.Cell3D([0.0, 0.0, 0.0], 1.0, 1.0)] * 64, 0.35)
+    np.testing.assert_allclose(T.L, np.cbrt(64 * 4.18879032) / 0.35, rtol=1e-6)
+    c2 = m.Cell2D(0.0, 0.0, 1.05, 32, 1.0)
+    np.testing.assert_allclose(np.asarray(c2.Verts)[0], [0.980785251, 0.195090324], rtol=2e-7)
+    T2 = m.Tissue2D([c2] * 32, 0.85)
+    np.testing.assert_allclose(T2.L, np.sqrt(32 * 3.12144494) / 0.85, rtol=1e-6)
+
+
+def test_cleulerupdate_validation_maps_to_reference_exceptions():
+    """src/Tissue3D.cpp:123-135 -> std::invalid_argument (ValueError); :159-171 -> std::runtime_error"""
+    m = H.cldpm()
+    c = m.Cell3D([0.0, 0.0, 1.0], 1.0, 1.0)
+    c.Kv, c.Ka, c.Ks = 5.0, 2.0, 3.0
+    T = m.Tissue3D([c] * 2, 0.35)
+    T.Kre = 25.0
+    with pytest.raises(ValueError, match="nsteps must be positive"):
+        T.CLEulerUpdate(0, 0.01)
+    with pytest.raises(ValueError, match="dt must be positive and reasonable"):
+        T.CLEulerUpdate(1, 0.5)
+    with pytest.raises(ValueError):
+        T.CLEulerUpdate(1, -0.01)
+    bad = m.Cell3D([0.0, 0.0, 1.0], 1.0, 1.0)  # Kv = Ka = 0 as constructed
+    T = m.Tissue3D([bad] * 2, 0.35)
+    with pytest.raises(RuntimeError, match="Invalid spring constants"):
+        T.CLEulerUpdate(1, 0.01)
+    nanc = m.Cell3D([0.0, 0.0, 1.0], 1.0, 1.0)
+    nanc.Kv, nanc.Ka, nanc.Ks = 5.0, 2.0, 3.0
+    v = nanc.Verts
+    v[5] = [float("nan"), 0.0, 0.0]
+    nanc.Verts = v
+    T = m.Tissue3D([nanc] * 2, 0.35)
+    with pytest.raises(RuntimeError, match="Non-finite vertex coordinates"):
+        T.CLEulerUpdate(1, 0.01)
+    if not has_gpu():
+        T = m.Tissue3D([c] * 2, 0.35)
+        with pytest.raises(RuntimeError):  # no device -> loud failure, never a CPU computation
+            T.CLEulerUpdate(1, 0.01)
+
+
+def test_disperse_separates_cells_and_keeps_shapes():
+    m = H.cldpm()
+    c = m.Cell2D(0.0, 0.0, 1.05, 32, 1.0)
+    T = m.Tissue2D([c] * 16, 0.85)
+    T.Disperse()
+    cells = T.Cells
+    ctr = np.array([np.asarray(x.Verts).mean(0) for x in cells])
+    d = ctr[:, None, :] - ctr[None, :, :]
+    d -= T.L * np.round(d / T.L)
+    dist = np.sqrt((d ** 2).sum(-1)) + 10 * np.eye(16)
+    assert dist.min() > 1.5  # soft discs of radius r0 relaxed apart (contact distance 2*r0)
+    r = np.linalg.norm(np.asarray(cells[3].Verts) - ctr[3], axis=1)
+    np.testing.assert_allclose(r, 1.0, rtol=1e-5)
+    c3 = m.Cell3D([0.0, 0.0, 0.0], 1.0, 1.0)
+    T3 = m.Tissue3D([c3] * 8, 0.35)
+    z0 = np.asarray(T3.Cells[0].Verts)[:, 2].copy()
+    T3.Disperse2D()
+    assert np.array_equal(np.asarray(T3.Cells[0].Verts)[:, 2], z0)  # z untouched (src/Tissue3D.cpp:106-115)
