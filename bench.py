@@ -177,7 +177,8 @@ def main():
     capi.lib()
     d = make_workload(args.workload, rank)
     dim = d["dim"]
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-legacy) stream: the library launches on it and the events are recorded on it
+    torch.cuda.set_stream(stream)
     nvert = d["nc"] * d["nv"] if dim == 3 else int(d["nv"].sum())
     balg = 32 if dim == 3 else 16
 
@@ -204,6 +205,7 @@ def main():
             return time.perf_counter() - t0
     else:
         h = Dpm2D(d["nc"], d["S"], device=local)
+        h.set_neighbor_params(0.1, 64)
         h.set_stream(stream.cuda_stream)
         params = [d[k] for k in PK2]
 

@@ -161,9 +161,9 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
         bool wantRep = false, wantAtt = false;
         if (act && doRep && !found) {
           const float dxl = p.x - bj0.x, dxh = p.x - bj1.x, dyl = p.y - bj0.y, dyh = p.y - bj1.y;
-          const bool in = dxl >= 0.0f && dxh <= 0.0f && dyl >= 0.0f && dyh <= 0.0f;
-          const bool far = P.pbc && (fabsf(dxl) > P.L || fabsf(dxh) > P.L || fabsf(dyl) > P.L || fabsf(dyh) > P.L);
-          wantRep = in || far;
+          const bool inx = dxl >= 0.0f && dxh <= 0.0f, iny = dyl >= 0.0f && dyh <= 0.0f;
+          const bool farx = P.pbc && (fabsf(dxl) > P.L || fabsf(dxh) > P.L), fary = P.pbc && (fabsf(dyl) > P.L || fabsf(dyh) > P.L);
+          wantRep = (inx || farx) && (iny || fary);
         }
         if (act && doAtt) {
           const float hx = 0.5f * (bj1.x - bj0.x), hy = 0.5f * (bj1.y - bj0.y);

@@ -54,10 +54,11 @@ struct Step3DParams {
 constexpr int UNIT_CAP_FACTOR = 2;  // unit list capacity = factor * THREADS
 // The reference skips faces with denom < 1e-8 (shaders/Cell3D_Kernel.cl:293-295): every face that subtends more
 // than pi steradians from the vertex.  Its winding number is therefore the true one (0 outside a closed mesh)
-// only if no face is that close.  A face with longest edge e lies in a ball of radius e around its point nearest
-// to p; that ball subtends < pi once dist > 2e/sqrt(3) = 1.1547 e.  A vertex farther than CONTACT_PAD * emax from a
-// cell's bounding box/sphere gets exactly zero repulsion from it and is culled.
-constexpr float CONTACT_PAD = 1.16f;
+// only if no face is that close.  Every point of a face lies within 2/3 of its longest median, hence within
+// (2/3) e of its centroid (e = longest edge); a ball of that radius subtends < pi steradians once the distance to
+// its centre exceeds (2/sqrt 3)(2/3) e = 0.7698 e.  Centroids lie inside the cell's bounding box/sphere, so a
+// vertex farther than CONTACT_PAD * emax from them gets exactly zero repulsion from that cell and is culled.
+constexpr float CONTACT_PAD = 0.775f;
 constexpr float RANGE_HEADROOM = 1.25f;  // lists are built for pads up to 1.25x the largest current one
 
 template <int THREADS>
@@ -251,7 +252,6 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
         const float4 Pn = sP[__ldg(rn + i)];
         const float3 E = sub3(Pn, Pv);
         const float len2 = dot3(E, E);
-        e2max = fmaxf(e2max, len2);
         const float rl = rsqrtf(len2);
         const float dl = len2 * rl * inv_l0 - 1.0f;  // len/l0 - 1  (:156-160)
         const int ip = (i == 0) ? val - 1 : i - 1;
@@ -339,15 +339,17 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
         const float4 p = sP[v];
         const float4 *Vj = P.pos_in + (size_t)cj * nv;
         float4 *myU = sU + (size_t)warp * nv;
-        const float ox = sh.x - p.x, oy = sh.y - p.y, oz = sh.z - p.z;
         for (int i = lane; i < nv; i += 32) {
           const float4 q = __ldg(Vj + i);
           // a = V + shift - p ; u = normalize(a)   (:285-291)
           const float ax = (q.x + sh.x) - p.x, ay = (q.y + sh.y) - p.y, az = (q.z + sh.z) - p.z;
-          const float r = rsqrtf(ax * ax + ay * ay + az * az);
+          // near-coplanar faces make the triple product cancel: refine MUFU.RSQ (2 ulp) with one Newton step so the
+          // unit vectors are as accurate as the reference's a / sqrt(dot(a, a))
+          const float d2 = ax * ax + ay * ay + az * az;
+          float r = rsqrtf(d2);
+          r = r * (1.5f - 0.5f * d2 * r * r);
           myU[i] = make_float4(ax * r, ay * r, az * r, 0.f);
         }
-        (void)ox; (void)oy; (void)oz;
         __syncwarp();
         float om = 0.0f;
         for (int f = lane; f < nf; f += 32) {
@@ -425,14 +427,11 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
   // ---- phase 4: Euler update, outputs, next-step bounds ------------------------------------------
   __syncthreads();  // everyone is done reading start-of-step sP
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  float d2max = 0.0f;
 #pragma unroll
   for (int j = 0; j < VPT; j++) {
     const int v = tid + j * THREADS;
     if (v < nv) {
       float4 np = myP[j];
-      const float ddx = F[j].x * P.dt, ddy = F[j].y * P.dt, ddz = F[j].z * P.dt;
-      d2max = fmaxf(d2max, ddx * ddx + ddy * ddy + ddz * ddz);
       np.x += F[j].x * P.dt; np.y += F[j].y * P.dt; np.z += F[j].z * P.dt;  // EulerPosition :380
       np.w = 0.f;
       P.pos_out[(size_t)ci * nv + v] = np;
@@ -444,11 +443,21 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
     }
   }
   for (int d = 0; d < 3; d++) { lo[d] = warp_min(lo[d]); hi[d] = warp_max(hi[d]); }
-  // upper bound of next step's longest edge: this step's longest edge + 2 * largest displacement
-  const float ebound = sqrtf(warp_max(e2max)) + 2.0f * sqrtf(warp_max(d2max));
-  if (lane == 0) { for (int d = 0; d < 3; d++) { sRed[warp][d] = lo[d]; sRed[warp][3 + d] = hi[d]; } sRed[warp][7] = ebound; }
+  if (lane == 0) for (int d = 0; d < 3; d++) { sRed[warp][d] = lo[d]; sRed[warp][3 + d] = hi[d]; }
   __syncthreads();
   if (warp == NW - 1 && lane < 3) sScalar[1 + lane] = com_chain(sP, nv, lane);
+  // longest edge of the NEW positions (sets next step's contact pad); overlaps the serial COM chain
+  e2max = 0.0f;
+#pragma unroll
+  for (int j = 0; j < VPT; j++) {
+    const int v = tid + j * THREADS;
+    if (v < nv) {
+      const int val = __ldg(P.valence + v);
+      const uint16_t *rn = P.ring_nbr + (size_t)v * P.ring_stride;
+      for (int i = 0; i < val; i++) { const float3 e = sub3(sP[__ldg(rn + i)], myP[j]); e2max = fmaxf(e2max, dot3(e, e)); }
+    }
+  }
+  e2max = warp_max(e2max);
   __syncthreads();
   const float3 ncom = f3(sScalar[1], sScalar[2], sScalar[3]);
   float r2 = 0.0f;
@@ -458,7 +467,7 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
     if (v < nv) { const float3 q = sub3(myP[j], ncom); r2 = fmaxf(r2, dot3(q, q)); }
   }
   r2 = warp_max(r2);
-  if (lane == 0) sRed[warp][6] = r2;
+  if (lane == 0) { sRed[warp][6] = r2; sRed[warp][7] = e2max; }
   __syncthreads();
   if (tid == 0) {
     float l[3], h[3], rr = sRed[0][6], eb = sRed[0][7];
@@ -466,9 +475,9 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
     for (int w = 1; w < NW; w++) {
       for (int d = 0; d < 3; d++) { l[d] = fminf(l[d], sRed[w][d]); h[d] = fmaxf(h[d], sRed[w][3 + d]); }
       rr = fmaxf(rr, sRed[w][6]);
-      eb = fmaxf(eb, sRed[w][7]);  // per-warp bounds are each >= the true per-warp maxima; their max bounds the cell
+      eb = fmaxf(eb, sRed[w][7]);
     }
-    const float pad = CONTACT_PAD * eb;
+    const float pad = CONTACT_PAD * sqrtf(eb);
     P.bnd_out[3 * (size_t)ci + 0] = make_float4(l[0], l[1], l[2], rr);
     P.bnd_out[3 * (size_t)ci + 1] = make_float4(h[0], h[1], h[2], pad);
     if (pad > P.st->range) P.st->rebuild = 1;  // the candidate lists were built for smaller contact pads

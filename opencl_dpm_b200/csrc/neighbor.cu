@@ -285,9 +285,13 @@ __global__ void __launch_bounds__(RB_THREADS) nbr_rebuild_kernel(NbrBuffers nb) 
         for (int j = 0; j < nb.nc; j++) {
           if (j == i) continue;
           const float4 loj = nb.blo[(size_t)j * nb.blo_stride], hij = nb.bhi[(size_t)j * nb.blo_stride];
-          const bool far = (__fsub_rn(hij.x, loi.x) > Lm) || (__fsub_rn(hii.x, loj.x) > Lm) ||
-                           (__fsub_rn(hij.y, loi.y) > Lm) || (__fsub_rn(hii.y, loj.y) > Lm);
-          if (!far) continue;
+          // per axis "overlap or far", and far on at least one axis (see oracle_cell_list)
+          const bool farx = (__fsub_rn(hij.x, loi.x) > Lm) || (__fsub_rn(hii.x, loj.x) > Lm);
+          const bool fary = (__fsub_rn(hij.y, loi.y) > Lm) || (__fsub_rn(hii.y, loj.y) > Lm);
+          if (!(farx || fary)) continue;
+          const bool ovx = !((__fsub_rn(loj.x, hii.x) > skin) || (__fsub_rn(loi.x, hij.x) > skin));
+          const bool ovy = !((__fsub_rn(loj.y, hii.y) > skin) || (__fsub_rn(loi.y, hij.y) > skin));
+          if (!((ovx || farx) && (ovy || fary))) continue;
           bool dup = false;
           for (int q = 0; q < min(n, KMAX); q++) dup |= (tmp[q] == j);
           if (!dup) { if (n < KMAX) tmp[n] = j; n++; }

@@ -174,12 +174,15 @@ void oracle_cell_list(int nd, int nc, const float *lo, const float *hi, int PBC,
       float Lm = L - skin;
       for (int j = 0; j < nc; j++) {
         if (j == i) continue;
-        int far = 0;
-        for (int d = 0; d < 2; d++) {
-          if (hi[3 * j + d] - lo[3 * i + d] > Lm) far = 1;
-          if (hi[3 * i + d] - lo[3 * j + d] > Lm) far = 1;
-        }
-        if (!far) continue;
+        /* The literal even-odd test can only report "inside" if, on EACH axis, the vertex lies within the
+         * polygon's extent or a |d| > L wrap can fire on that axis (no y-straddle otherwise; all x-crossings on
+         * one side otherwise).  Cell level, with the skin: per axis "overlap or far", and far on >= 1 axis. */
+        int farx = (hi[3 * j] - lo[3 * i] > Lm) || (hi[3 * i] - lo[3 * j] > Lm);
+        int fary = (hi[3 * j + 1] - lo[3 * i + 1] > Lm) || (hi[3 * i + 1] - lo[3 * j + 1] > Lm);
+        if (!(farx || fary)) continue;
+        int ovx = !((lo[3 * j] - hi[3 * i] > skin) || (lo[3 * i] - hi[3 * j] > skin));
+        int ovy = !((lo[3 * j + 1] - hi[3 * i + 1] > skin) || (lo[3 * i + 1] - hi[3 * j + 1] > skin));
+        if (!((ovx || farx) && (ovy || fary))) continue;
         int dup = 0;
         for (int q = 0; q < n; q++) if (tmp[q] == j) { dup = 1; break; }
         if (!dup) tmp[n++] = j;

@@ -238,11 +238,12 @@ static void FN(forces3d_range)(int nc, int nv, int nf, const uint32_t *faces, co
           if (cand) {
             /* exact per-vertex cull.  The reference drops every face with denom < 1e-8, i.e. every face that
              * subtends more than pi steradians (:293-295), so its "winding number" is the true one (0 outside)
-             * only when no face is that close: a face of longest edge e lies in a ball of radius e around its
-             * point nearest to p, which subtends < pi once dist > 2e/sqrt(3) = 1.1547 e.  Hence: p farther than
-             * 1.16 * emax(cj) from the (shifted) AABB of cj => every denom > 0 and wn == 0 in exact arithmetic. */
+             * only when no face is that close.  A face lies within (2/3) e of its centroid (e = its longest edge);
+             * a ball of that radius subtends < pi beyond (2/sqrt 3)(2/3) e = 0.7698 e from its centre, and all
+             * centroids are inside the cell's AABB.  Hence: p farther than 0.775 * emax(cj) from the (shifted)
+             * AABB of cj => every denom > 0 and wn == 0 in exact arithmetic. */
             int out = 0;
-            REAL pad = (REAL)1.16f * emax[cj];
+            REAL pad = (REAL)0.775f * emax[cj];
             for (int d = 0; d < 3; d++) {
               REAL sh = PBC ? L * RROUND((comi[d] - comj[d]) / L) : (REAL)0.0;
               REAL l = (lo[3 * cj + d] + sh) - pad, h = (hi[3 * cj + d] + sh) + pad;
@@ -420,9 +421,9 @@ void FN(oracle2d_forces)(int nc, int S, const int32_t *NV, const REAL *verts, RE
           if (cand) {
             /* per-vertex cull, exact: evaluate iff p in AABB(cj) or some |d|>L can occur */
             REAL dxl = p[0] - lo[2 * cj], dxh = p[0] - hi[2 * cj], dyl = p[1] - lo[2 * cj + 1], dyh = p[1] - hi[2 * cj + 1];
-            int in = (dxl >= 0 && dxh <= 0 && dyl >= 0 && dyh <= 0);
-            int far = PBC && (RABS(dxl) > L || RABS(dxh) > L || RABS(dyl) > L || RABS(dyh) > L);
-            if (!in && !far) continue;
+            int inx = (dxl >= 0 && dxh <= 0), iny = (dyl >= 0 && dyh <= 0);
+            int farx = PBC && (RABS(dxl) > L || RABS(dxh) > L), fary = PBC && (RABS(dyl) > L || RABS(dyh) > L);
+            if (!((inx || farx) && (iny || fary))) continue;
           }
           overlaps = FN(inside2d)(p, verts + 2 * (size_t)cj * S, NV[cj], PBC, L);
         }
