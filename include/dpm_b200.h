@@ -106,6 +106,14 @@ int dpm3d_set_stream(dpm3d_t *h, void *cuda_stream);
  * max_candidates: per-cell candidate-list capacity K (default 32). Takes effect at the next upload. */
 int dpm3d_set_neighbor_params(dpm3d_t *h, float skin_rel, int max_candidates);
 int dpm3d_set_force_mask(dpm3d_t *h, unsigned mask);
+/* Reference-race compatibility (off by default).  VolumeForceUpdate writes cellVolumes[ci] from work-item fi==0
+ * and reads it back behind a work-group-scoped barrier (shaders/Cell3D_Kernel.cl:74-83) while the launch leaves
+ * the local size to the runtime (src/Tissue3D.cpp:383): on NVIDIA's OpenCL the local size is 160, so faces
+ * 160..319 read the volume of the PREVIOUS step (0 on the first step of every CLEulerUpdate call).  The default
+ * (stale_volume_from_face < 0) implements the intended semantics — every face sees the current volume;
+ * dpm3d_set_compat(h, 160) reproduces what the reference actually computes on NVIDIA hardware, bit-for-bit in
+ * structure, so the CUDA path can be compared with the reference's own outputs (tests/golden). */
+int dpm3d_set_compat(dpm3d_t *h, int stale_volume_from_face);
 
 /* verts4: ncells*nv*4 floats (x,y,z,pad).  Per-cell arrays of length ncells:
  * Kv,Ka,Ks (src/Tissue3D.cpp:172-174), v0,a0 (:175-176), l0 = sqrt(4 a0)/sqrt(3) (:177). */

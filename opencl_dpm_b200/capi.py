@@ -128,6 +128,10 @@ class Dpm3D:
     def set_force_mask(self, mask: int):
         _check(lib().dpm3d_set_force_mask(self._h, C.c_uint(mask)))
 
+    def set_compat(self, stale_volume_from_face: int = -1):
+        """>= 0: reproduce the reference's volume race as it resolves on NVIDIA OpenCL (see include/dpm_b200.h)."""
+        _check(lib().dpm3d_set_compat(self._h, int(stale_volume_from_face)))
+
     def _params(self, Kv, Ka, Ks, v0, a0, l0):
         return [_f32(np.broadcast_to(np.asarray(x, np.float32), (self.nc,)), self.nc) for x in (Kv, Ka, Ks, v0, a0, l0)]
 

@@ -43,6 +43,7 @@ struct dpm3d_ctx {
   dpm_stats_t stats{};
   int last_pbc = -1;
   float last_L = -1.f;
+  int stale_from = -1;
 };
 
 namespace {
@@ -278,6 +279,12 @@ int dpm3d_set_neighbor_params(dpm3d_t *h, float skin_rel, int max_candidates) {
   return DPM_OK;
 }
 
+int dpm3d_set_compat(dpm3d_t *h, int stale_volume_from_face) {
+  if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
+  h->stale_from = stale_volume_from_face < 0 ? -1 : stale_volume_from_face;
+  return DPM_OK;
+}
+
 int dpm3d_set_force_mask(dpm3d_t *h, unsigned mask) {
   if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
   h->mask = mask & DPM3D_ALL;
@@ -345,6 +352,7 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
   p.cand_count = h->cand_count; p.cand = h->cand; p.K = h->K;
   p.bbox_lo = h->bbox_lo; p.bbox_hi = h->bbox_hi; p.st = h->st;
   p.nc = h->nc; p.nv = h->nv; p.nf = h->nf; p.dt = dt; p.Kc = Kre; p.pbc = pbc; p.L = L; p.mask = h->mask;
+  p.stale_from = h->stale_from;
   if (pbc != h->last_pbc || L != h->last_L) {  // the lists depend on the box: rebuild when the caller changed it
     static const int one = 1;
     DPM_CUDA_TRY(cudaMemcpyAsync(&h->st->rebuild, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));

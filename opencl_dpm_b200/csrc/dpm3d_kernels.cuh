@@ -49,6 +49,7 @@ struct Step3DParams {
   int pbc;
   float L;
   unsigned mask;
+  int stale_from;  // >= 0: reference-race compatibility mode (dpm3d_set_compat), else -1
 };
 
 constexpr int UNIT_CAP_FACTOR = 2;  // unit list capacity = factor * THREADS
@@ -232,13 +233,14 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
   // ---- phase 2b: ring pass (edge springs + volume gradient + flag gather) ---------------------
   const float inv_l0 = 1.0f / l0;
   int ndown[VPT];
-  float3 G[VPT];
+  float3 G[VPT], Gs[VPT];  // volume gradient: all ring faces / ring faces with index >= stale_from (compat mode)
   float e2max = 0.0f;
 #pragma unroll
   for (int j = 0; j < VPT; j++) {
     const int v = tid + j * THREADS;
     ndown[j] = 0;
     G[j] = f3(0.f, 0.f, 0.f);
+    Gs[j] = f3(0.f, 0.f, 0.f);
     if (v < nv) {
       const int val = __ldg(P.valence + v);
       const uint16_t *rn = P.ring_nbr + (size_t)v * P.ring_stride;
@@ -261,10 +263,18 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
         T.x += E.x * s; T.y += E.y * s; T.z += E.z * s;
         const float3 Q = sub3(Pn, com);
         if (i == 0) Q0 = Q;
-        else { float3 c = cross3(Qp, Q); g.x += c.x; g.y += c.y; g.z += c.z; }
+        else {
+          const float3 c = cross3(Qp, Q);  // gradient of ring face i-1 = (v, n_{i-1}, n_i)
+          g.x += c.x; g.y += c.y; g.z += c.z;
+          if (P.stale_from >= 0 && (int)__ldg(rf + i - 1) >= P.stale_from) { Gs[j].x += c.x; Gs[j].y += c.y; Gs[j].z += c.z; }
+        }
         Qp = Q;
       }
-      { float3 c = cross3(Qp, Q0); g.x += c.x; g.y += c.y; g.z += c.z; }
+      {
+        const float3 c = cross3(Qp, Q0);  // ring face val-1 = (v, n_{val-1}, n_0)
+        g.x += c.x; g.y += c.y; g.z += c.z;
+        if (P.stale_from >= 0 && (int)__ldg(rf + val - 1) >= P.stale_from) { Gs[j].x += c.x; Gs[j].y += c.y; Gs[j].z += c.z; }
+      }
       G[j] = g;
       if ((P.mask & DPM3D_AREA) && !(Ka < 1e-8f)) {
         const float scale = Ka * sqrtf(a0) / l0 * 0.3f;  // :162
@@ -278,12 +288,16 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
   {
     const float volume = sScalar[0];
     const float coef = doVol ? (-Kv * (volume / v0 - 1.0f)) * (1.0f / 6.0f) : 0.0f;  // :85,:106-108
+    // compat mode: faces >= stale_from see the volume of the previous step's start (0 right after an upload)
+    const float dcoef = (doVol && P.stale_from >= 0) ? (-Kv * (bi2.w / v0 - 1.0f)) * (1.0f / 6.0f) - coef : 0.0f;
     const bool doStick = (P.mask & DPM3D_STICK) && !(Ks < 1e-12f);
 #pragma unroll
     for (int j = 0; j < VPT; j++) {
       const int v = tid + j * THREADS;
       if (v < nv) {
-        F[j].x += coef * G[j].x; F[j].y += coef * G[j].y; F[j].z += coef * G[j].z;
+        F[j].x += coef * G[j].x + dcoef * Gs[j].x;
+        F[j].y += coef * G[j].y + dcoef * Gs[j].y;
+        F[j].z += coef * G[j].z + dcoef * Gs[j].z;
         if (doStick && ndown[j] > 0) {
           const float4 Pv = myP[j];
           const float nd = (float)ndown[j];  // one application per adjacent down-facing face (:226-246)

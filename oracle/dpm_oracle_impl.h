@@ -65,10 +65,17 @@ static REAL FN(volume3d)(const REAL *V, const uint32_t *F, int nf) {
 
 /* shaders/Cell3D_Kernel.cl:66-112  VolumeForceUpdate (volume = current
  * positions). */
-static void FN(volume_force3d)(const REAL *V, REAL *Fo, const uint32_t *F, int nv, int nf, REAL Kv, REAL v0) {
+/* stale_from >= 0 emulates the work-group race of the reference as it resolves on NVIDIA's OpenCL:
+ * the runtime picks a local size of nf/2 = 160, the barrier is work-group scoped, so faces >= stale_from read
+ * cellVolumes[ci] BEFORE work-item 0 of the other group writes it: the previous step's volume (0 on the first
+ * step of a call, src/Tissue3D.cpp:180).  stale_from < 0: intended semantics (current volume for every face). */
+static void FN(volume_force3d)(const REAL *V, REAL *Fo, const uint32_t *F, int nv, int nf, REAL Kv, REAL v0,
+                               int stale_from, REAL *prev_volume) {
   if (Kv == (REAL)0.0) return;
   REAL volume = FN(volume3d)(V, F, nf);
-  REAL strain = (volume / v0) - (REAL)1.0;
+  REAL strain_fresh = (volume / v0) - (REAL)1.0;
+  REAL strain_stale = strain_fresh;
+  if (stale_from >= 0 && prev_volume) { strain_stale = (*prev_volume / v0) - (REAL)1.0; *prev_volume = volume; }
   REAL com[3]; FN(com3d)(V, nv, com);
   for (int fi = 0; fi < nf; fi++) {
     uint32_t i0 = F[3 * fi], i1 = F[3 * fi + 1], i2 = F[3 * fi + 2];
@@ -79,6 +86,7 @@ static void FN(volume_force3d)(const REAL *V, REAL *Fo, const uint32_t *F, int n
       C[d] = V[4 * i0 + d] - com[d];
     }
     FN(cross3)(A, B, g0); FN(cross3)(B, C, g1); FN(cross3)(C, A, g2);
+    REAL strain = (stale_from >= 0 && fi >= stale_from) ? strain_stale : strain_fresh;
     REAL coef = -Kv * strain; /* (-Kv*strain)*grad/6 : :106-108 */
     for (int d = 0; d < 3; d++) {
       Fo[4 * i0 + d] += coef * g0[d] / (REAL)6.0;
@@ -192,7 +200,8 @@ static inline REAL FN(repel_pair3d)(const REAL *Vj, const uint32_t *F, int nf, c
 static void FN(forces3d_range)(int nc, int nv, int nf, const uint32_t *faces, const REAL *verts, REAL *forces,
                                const REAL *Kv, const REAL *Ka, const REAL *Ks, const REAL *v0, const REAL *a0,
                                const REAL *l0, REAL Kc, int PBC, REAL L, int which, const int32_t *cand_count,
-                               const int32_t *cand, int cand_stride, int32_t *contacts, int c0, int c1) {
+                               const int32_t *cand, int cand_stride, int32_t *contacts, int c0, int c1,
+                               int stale_from, REAL *prev_volumes) {
   /* ClearForces :366-369 */
   memset(forces, 0, sizeof(REAL) * 4 * (size_t)nc * nv);
   REAL *coms = (REAL *)malloc(sizeof(REAL) * 3 * nc);
@@ -219,7 +228,7 @@ static void FN(forces3d_range)(int nc, int nv, int nf, const uint32_t *faces, co
       if (x > hi[3 * ci + d]) hi[3 * ci + d] = x;
     }
     if (ci < c0 || ci >= c1) continue; /* bounds/COM are needed for every cell, forces only for [c0,c1) */
-    if (which & 1) FN(volume_force3d)(V, Fo, faces, nv, nf, Kv[ci], v0[ci]);
+    if (which & 1) FN(volume_force3d)(V, Fo, faces, nv, nf, Kv[ci], v0[ci], stale_from, prev_volumes ? prev_volumes + ci : NULL);
     if (which & 2) FN(area_force3d)(V, Fo, faces, nf, Ka[ci], a0[ci], l0[ci]);
     if (which & 4) FN(stick_force3d)(V, Fo, faces, nv, nf, Ks[ci], l0[ci]);
   }
@@ -269,7 +278,7 @@ void FN(oracle3d_forces)(int nc, int nv, int nf, const uint32_t *faces, const RE
                          const REAL *l0, REAL Kc, int PBC, REAL L, int which,
                          const int32_t *cand_count, const int32_t *cand, int cand_stride, int32_t *contacts) {
   FN(forces3d_range)(nc, nv, nf, faces, verts, forces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, which, cand_count, cand,
-                     cand_stride, contacts, 0, nc);
+                     cand_stride, contacts, 0, nc, -1, NULL);
 }
 
 /* Same, but forces are evaluated only for cells [c0, c1) (against ALL cells): a bounded sample of the
@@ -278,7 +287,7 @@ void FN(oracle3d_forces_range)(int nc, int nv, int nf, const uint32_t *faces, co
                                const REAL *Kv, const REAL *Ka, const REAL *Ks, const REAL *v0, const REAL *a0,
                                const REAL *l0, REAL Kc, int PBC, REAL L, int which, int c0, int c1) {
   FN(forces3d_range)(nc, nv, nf, faces, verts, forces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, which, NULL, NULL, 0, NULL,
-                     c0, c1);
+                     c0, c1, -1, NULL);
 }
 
 /* EulerPosition :371-381 */
@@ -296,6 +305,20 @@ void FN(oracle3d_run)(int nc, int nv, int nf, const uint32_t *faces, REAL *verts
     FN(oracle3d_forces)(nc, nv, nf, faces, verts, forces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, which, NULL, NULL, 0, NULL);
     FN(oracle3d_euler)(nc, nv, verts, forces, dt);
   }
+}
+
+/* One CLEulerUpdate call of the reference AS IT EXECUTES on NVIDIA's OpenCL: faces >= stale_from use the volume
+ * of the previous step (zero on the first step of the call) — see volume_force3d. */
+void FN(oracle3d_run_compat)(int nc, int nv, int nf, const uint32_t *faces, REAL *verts, REAL *forces, const REAL *Kv,
+                             const REAL *Ka, const REAL *Ks, const REAL *v0, const REAL *a0, const REAL *l0, REAL Kc,
+                             int PBC, REAL L, int nsteps, REAL dt, int which, int stale_from) {
+  REAL *prev = (REAL *)calloc(nc, sizeof(REAL));
+  for (int s = 0; s < nsteps; s++) {
+    FN(forces3d_range)(nc, nv, nf, faces, verts, forces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, which, NULL, NULL, 0, NULL,
+                       0, nc, stale_from, prev);
+    FN(oracle3d_euler)(nc, nv, verts, forces, dt);
+  }
+  free(prev);
 }
 
 /* ======================================================================== */

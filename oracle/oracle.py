@@ -89,8 +89,10 @@ def forces3d_range(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, c0, c1, wh
     return Fo
 
 
-def run3d(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, nsteps, dt, which=15, dtype=np.float32):
-    """nsteps of the all-pairs reference algorithm. Returns (verts4, last_forces4)."""
+def run3d(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, nsteps, dt, which=15, dtype=np.float32, stale_from=-1):
+    """nsteps of the all-pairs reference algorithm. Returns (verts4, last_forces4).
+    stale_from >= 0: emulate the reference's volume race as it resolves on NVIDIA OpenCL (faces >= stale_from use
+    the previous step's volume, zero on the first step of the call)."""
     ct, sfx = _real(dtype)
     faces = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
     nf = faces.shape[0]
@@ -99,6 +101,12 @@ def run3d(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, nsteps, dt, which=1
     nv = V.shape[0] // nc
     Fo = np.zeros_like(V)
     P = [_arr(x, nc, dtype) for x in (Kv, Ka, Ks, v0, a0, l0)]
+    if stale_from >= 0:
+        fn = getattr(lib(), "oracle3d_run_compat" + sfx)
+        fn.restype = None
+        fn(nc, nv, nf, _p(faces, C.c_uint32), _p(V, ct), _p(Fo, ct), *[_p(x, ct) for x in P], ct(Kc), int(PBC), ct(L),
+           int(nsteps), ct(dt), int(which), int(stale_from))
+        return V, Fo
     fn = getattr(lib(), "oracle3d_run" + sfx)
     fn.restype = None
     fn(nc, nv, nf, _p(faces, C.c_uint32), _p(V, ct), _p(Fo, ct), *[_p(x, ct) for x in P], ct(Kc), int(PBC), ct(L),

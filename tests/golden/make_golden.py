@@ -1,0 +1,68 @@
+"""Generates the golden vectors in tests/golden/*.npz by running the REAL reference (oracle/_ref: the reference's
+own host code and OpenCL kernels on NVIDIA's OpenCL) — run on the GPU box:
+
+    gpurun -- 'python tests/golden/make_golden.py gpurun_out/golden'
+
+and copy gpurun_out/golden/*.npz into tests/golden/.  Inputs are the reference's demo configurations, built with
+the reference's own constructors and Disperse()/Disperse2D() (unseeded drand48 re-armed to its initial state).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref as R  # noqa: E402
+
+
+def golden3d(name, ncells, start, calA, r0, phi0, Kv, Ka, Ks, Kre, dt, steps_list, out):
+    verts3, L = R.disperse3d(ncells, start, calA, r0, phi0)
+    _, faces, sc = R.cell3d(start, calA, r0)
+    V0 = np.zeros((ncells * 162, 4), np.float32)
+    V0[:, :3] = verts3
+    res = dict(verts0=V0, faces=faces, L=L, PBC=1, Kv=np.float32(Kv), Ka=np.float32(Ka), Ks=np.float32(Ks), v0=sc["v0"], a0=sc["a0"],
+               Kre=np.float32(Kre), dt=np.float32(dt), steps=np.array(steps_list))
+    for n in steps_list:
+        V, F, sec = R.euler3d(V0, Kv, Ka, Ks, sc["v0"], sc["a0"], Kre, 1, L, n, dt)
+        res[f"verts_{n}"], res[f"forces_{n}"] = V, F
+        print(name, n, "steps:", f"{sec:.3f}s", "|F|max", np.abs(F).max())
+    np.savez_compressed(os.path.join(out, name + ".npz"), **res)
+
+
+def golden2d(name, specs, phi0, Ka, Kl, Kb, Kre, Kat, dt, steps_list, out):
+    """specs: list of (calA, nv, r0) prototypes, tiled like the reference demos."""
+    cells = [R.cell2d(0.0, 0.0, *s) for s in specs]
+    nvs = np.array([s[1] for s in specs], np.int32)
+    S = int(nvs.max())
+    n = len(specs)
+    # the reference's Disperse for mixed tissues: replicate by building the tissue through its own code path
+    import ctypes as C
+
+    # Disperse only depends on r0 and L; use the uniform helper when all prototypes are equal
+    assert len(set(specs)) == 1, "golden2d: uniform tissues only (mixed ones are covered by GPU-vs-oracle tests)"
+    verts, L = R.disperse2d(n, specs[0][0], specs[0][1], specs[0][2], phi0)
+    V0 = np.zeros((n, S, 2), np.float32)
+    V0[:, :S] = verts
+    sc = cells[0][1]
+    res = dict(verts0=V0, nv=nvs, L=L, PBC=1, Ka=np.float32(Ka), Kl=np.float32(Kl), Kb=np.float32(Kb), a0=sc["a0"], l0=sc["l0"],
+               r0=np.float32(specs[0][2]), Kre=np.float32(Kre), Kat=np.float32(Kat), dt=np.float32(dt), steps=np.array(steps_list))
+    for k in steps_list:
+        V, F, sec = R.euler2d(V0, nvs, Ka, Kl, Kb, sc["a0"], sc["l0"], specs[0][2], Kre, Kat, 1, L, k, dt)
+        res[f"verts_{k}"], res[f"forces_{k}"] = V, F
+        print(name, k, "steps:", f"{sec:.3f}s", "|F|max", np.abs(F).max())
+    np.savez_compressed(os.path.join(out, name + ".npz"), **res)
+
+
+if __name__ == "__main__":
+    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
+    os.makedirs(out, exist_ok=True)
+    if not R.available():
+        raise SystemExit("no OpenCL device: run this on the GPU box")
+    print("reference device:", R.device_name())
+    # reference test3D.py (16 cells to keep the fixture small) and test3D.cpp's cell type
+    golden3d("ref3d_test3dpy_16", 16, [0.0, 0.0, 0.0], 1.0, 1.0, 0.35, 5.0, 2.0, 3.0, 25.0, 0.01, [1, 10], out)
+    golden3d("ref3d_test3dcpp_12", 12, [7.0, 6.0, 1.3], 1.05, 1.8, 0.35, 1.0, 1.0, 1.0, 50.0, 0.005, [1, 25], out)
+    # reference test2D.cpp (32 cells = BASELINE config A) and a Kat != 0 variant
+    golden2d("ref2d_test2d_32", [(1.05, 32, 1.0)] * 32, 0.85, 1.0, 1.0, 0.1, 50.0, 0.0, 0.005, [1, 20], out)
+    golden2d("ref2d_kat_24", [(1.2, 25, 1.0)] * 24, 0.9, 0.1, 1.0, 0.05, 1.0, 0.5, 0.005, [1, 20], out)
