@@ -156,9 +156,14 @@ int dpm3d_reset_stats(dpm3d_t *h);
 /* 128-byte NCCL unique id: rank 0 calls dpm_nccl_unique_id and broadcasts the bytes
  * (torch.distributed / MPI / a file); every rank then calls dpm3d_shard_init. */
 int dpm_nccl_unique_id(uint8_t id[128]);
-/* The handle owns ncells LOCAL cells (its slab); max_ghost is the capacity for ghost
- * cells received from the two neighbouring slabs. */
+/* Turns a fresh handle into one shard: its ncells are the cells OWNED by this rank (any static assignment is
+ * correct; x-slabs keep the halo small); max_ghost = ghost cells accepted from EACH of the two neighbouring
+ * slabs.  Call before the first upload, on every rank (it creates the NCCL communicator).  Afterwards
+ * dpm3d_step exchanges the boundary cells' vertices with ncclSend/ncclRecv before every timestep. */
 int dpm3d_shard_init(dpm3d_t *h, int rank, int nranks, const uint8_t id[128], int max_ghost);
+/* Global ids of the owned cells; candidate lists are ordered by global id so that a sharded run sums forces in
+ * the single-GPU order (bit-identical results). */
+int dpm3d_set_global_ids(dpm3d_t *h, const int32_t *gid);
 
 /* ---- 2D:  replaces shaders/Cell2D_kernel.cl + src/Tissue2D.cpp:142-233 ---- */
 int dpm2d_create(dpm2d_t **h, int device, int ncells, int max_nv);

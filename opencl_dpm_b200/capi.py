@@ -79,6 +79,12 @@ def device_count() -> int:
     return n.value
 
 
+def nccl_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    _check(lib().dpm_nccl_unique_id(buf))
+    return bytes(buf)
+
+
 def icosphere(subdiv: int = 2):
     nv, nf = 10 * 4 ** subdiv + 2, 20 * 4 ** subdiv
     V = np.zeros((nv, 3), np.float32)
@@ -127,6 +133,15 @@ class Dpm3D:
 
     def set_force_mask(self, mask: int):
         _check(lib().dpm3d_set_force_mask(self._h, C.c_uint(mask)))
+
+    def shard_init(self, rank: int, nranks: int, unique_id: bytes, max_ghost: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(lib().dpm3d_shard_init(self._h, int(rank), int(nranks), buf, int(max_ghost)))
+
+    def set_global_ids(self, gid):
+        g = np.ascontiguousarray(gid, dtype=np.int32)
+        assert g.size == self.nc
+        _check(lib().dpm3d_set_global_ids(self._h, _ip(g)))
 
     def set_compat(self, stale_volume_from_face: int = -1):
         """>= 0: reproduce the reference's volume race as it resolves on NVIDIA OpenCL (see include/dpm_b200.h)."""

@@ -8,43 +8,9 @@
 #include <map>
 #include <vector>
 
-#include "dpm3d_kernels.cuh"
+#include "dpm3d_ctx.cuh"
 
 using namespace dpm;
-
-struct dpm3d_ctx {
-  int device = 0;
-  int nc = 0, nv = 0, nf = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  float4 *pos[2] = {nullptr, nullptr};
-  float4 *force = nullptr;
-  float4 *bnd[2] = {nullptr, nullptr};
-  float4 *cellA = nullptr, *cellB = nullptr;
-  ushort4 *faces = nullptr;
-  uint16_t *ring_nbr = nullptr, *ring_face = nullptr;
-  uint8_t *valence = nullptr;
-  int ring_stride = 0;
-  // neighbour search
-  NbrState *st = nullptr;
-  float4 *bbox_lo = nullptr, *bbox_hi = nullptr;
-  int *bin_id = nullptr, *order = nullptr, *bin_count = nullptr, *bin_start = nullptr, *cand_count = nullptr, *cand = nullptr;
-  float *partial = nullptr;
-  int *chunk_sum = nullptr;
-  int cap = 0, K = 32, K_alloc = 0;
-  float skin_rel = 0.1f;
-  int coop_grid = 0;
-  int cur = 0;
-  unsigned mask = DPM3D_ALL;
-  bool uploaded = false;
-  int threads = 0, vpt = 0;
-  size_t smem = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  float4 *h_cell = nullptr;  // pinned staging for per-cell parameters
-  dpm_stats_t stats{};
-  int last_pbc = -1;
-  float last_L = -1.f;
-  int stale_from = -1;
-};
 
 namespace {
 
@@ -152,6 +118,8 @@ NbrBuffers nbr_buffers(dpm3d_ctx *h, int pbc, float L) {
   nb.cand_count = h->cand_count; nb.cand = h->cand;
   nb.partial = h->partial; nb.chunk_sum = h->chunk_sum;
   nb.nc = h->nc; nb.nc_list = h->nc; nb.nd = 3; nb.cap = h->cap; nb.K = h->K;
+  nb.nc_dev = h->nranks > 1 ? reinterpret_cast<const int *>(h->sd) : nullptr;  // ShardDev::n_total is its first member
+  nb.gid = h->gid;
   nb.pbc = pbc; nb.L = L; nb.skin_rel = h->skin_rel; nb.range = 0.0f; nb.far2d = 0;
   nb.range_from_bounds = 1; nb.range_scale = RANGE_HEADROOM;
   return nb;
@@ -185,7 +153,7 @@ int dpm3d_create(dpm3d_t **out, int device, int ncells, int nv, int nf, const ui
   if (rc) return rc;
   DeviceGuard guard(device);
   dpm3d_ctx *h = new dpm3d_ctx();
-  h->device = device; h->nc = ncells; h->nv = nv; h->nf = nf; h->ring_stride = stride;
+  h->device = device; h->nc = ncells; h->nslots = ncells; h->nv = nv; h->nf = nf; h->ring_stride = stride;
   rc = pick_config(h);
   if (rc) { delete h; return rc; }
   auto bail = [&](int code) { dpm3d_destroy(h); return code; };
@@ -246,6 +214,7 @@ int dpm3d_destroy(dpm3d_t *h) {
   if (!h) return DPM_OK;
   DeviceGuard guard(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  shard_free(h);
   void *ptrs[] = {h->pos[0], h->pos[1], h->force, h->bnd[0], h->bnd[1], h->cellA, h->cellB, h->faces, h->ring_nbr, h->ring_face,
                   h->valence, h->st, h->bbox_lo, h->bbox_hi, h->bin_id, h->order, h->bin_count, h->bin_start, h->cand_count,
                   h->cand, h->partial, h->chunk_sum};
@@ -359,6 +328,10 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
     h->last_pbc = pbc; h->last_L = L;
   }
   for (int s = 0; s < nsteps; s++) {
+    if (h->nranks > 1) {  // ghosts of the current state + the global rebuild decision (dpm_halo.cu)
+      int rc = shard_exchange(h, pbc, L);
+      if (rc) return rc;
+    }
     DPM_CUDA_TRY(launch_rebuild(nbr_buffers(h, pbc, L), h->stream, h->coop_grid));
     p.pos_in = h->pos[h->cur]; p.pos_out = h->pos[h->cur ^ 1];
     p.bnd_in = h->bnd[h->cur]; p.bnd_out = h->bnd[h->cur ^ 1];
@@ -378,6 +351,7 @@ static int check_device_flags(dpm3d_t *h) {
   h->stats.rebuilds = (uint64_t)st.nbuilds;
   h->stats.contact_evals = st.contact_evals;
   if (st.overflow) return fail(DPM_ERR_RUNTIME, "neighbour candidate list overflow: raise max_candidates (dpm3d_set_neighbor_params)");
+  if (h->nranks > 1) return shard_check(h);
   return DPM_OK;
 }
 
@@ -463,15 +437,6 @@ int dpm3d_reset_stats(dpm3d_t *h) {
   if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
   memset(&h->stats, 0, sizeof(h->stats));
   return DPM_OK;
-}
-
-int dpm_nccl_unique_id(uint8_t id[128]) {
-  (void)id;
-  return fail(DPM_ERR_NCCL, "multi-GPU path not built in this revision");
-}
-int dpm3d_shard_init(dpm3d_t *h, int rank, int nranks, const uint8_t id[128], int max_ghost) {
-  (void)h; (void)rank; (void)nranks; (void)id; (void)max_ghost;
-  return fail(DPM_ERR_NCCL, "multi-GPU path not built in this revision");
 }
 
 }  // extern "C"

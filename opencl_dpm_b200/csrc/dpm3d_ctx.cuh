@@ -1,0 +1,64 @@
+// dpm3d_ctx.cuh — the 3D handle, shared by dpm3d.cu (single-GPU path) and dpm_halo.cu (slab sharding).
+#pragma once
+#include "dpm3d_kernels.cuh"
+
+namespace dpm {
+struct ShardDev;  // device-side sharding state (dpm_halo.cu)
+}
+
+using dpm::NbrState;
+
+struct dpm3d_ctx {
+  int device = 0;
+  int nc = 0, nv = 0, nf = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  float4 *pos[2] = {nullptr, nullptr};
+  float4 *force = nullptr;
+  float4 *bnd[2] = {nullptr, nullptr};
+  float4 *cellA = nullptr, *cellB = nullptr;
+  ushort4 *faces = nullptr;
+  uint16_t *ring_nbr = nullptr, *ring_face = nullptr;
+  uint8_t *valence = nullptr;
+  int ring_stride = 0;
+  // neighbour search
+  NbrState *st = nullptr;
+  float4 *bbox_lo = nullptr, *bbox_hi = nullptr;
+  int *bin_id = nullptr, *order = nullptr, *bin_count = nullptr, *bin_start = nullptr, *cand_count = nullptr, *cand = nullptr;
+  float *partial = nullptr;
+  int *chunk_sum = nullptr;
+  int cap = 0, K = 32, K_alloc = 0;
+  float skin_rel = 0.1f;
+  int coop_grid = 0;
+  int cur = 0;
+  unsigned mask = DPM3D_ALL;
+  bool uploaded = false;
+  int threads = 0, vpt = 0;
+  size_t smem = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float4 *h_cell = nullptr;  // pinned staging for per-cell parameters
+  dpm_stats_t stats{};
+  int last_pbc = -1;
+  float last_L = -1.f;
+  int stale_from = -1;
+  // ---- slab sharding (dpm_halo.cu); nranks == 1 means unsharded -------------------------------------------
+  int nslots = 0;  // allocated cell slots: owned cells + ghost capacity (== nc when unsharded)
+  int rank = 0, nranks = 1;
+  void *comm = nullptr;  // ncclComm_t
+  int npeers = 0, peer[2] = {-1, -1};
+  int ghost_cap = 0;  // ghost cells accepted from each peer
+  int *gid = nullptr;  // [nslots] global cell ids (owned: set by dpm3d_set_global_ids, ghosts: from the halo messages)
+  dpm::ShardDev *sd = nullptr;
+  float *gather_send = nullptr, *gather_all = nullptr;
+  unsigned char *sendbuf[2] = {nullptr, nullptr}, *recvbuf[2] = {nullptr, nullptr};
+  int *sendlist[2] = {nullptr, nullptr};
+  size_t msg_bytes = 0;
+};
+
+namespace dpm {
+// one halo exchange of the CURRENT state (pos[cur], bnd[cur]) + global rebuild decision; no-op when unsharded
+int shard_exchange(dpm3d_ctx *h, int pbc, float L);
+int shard_check(dpm3d_ctx *h);   // after a sync: sharding errors (ghost overflow, slabs too thin)
+void shard_free(dpm3d_ctx *h);
+}  // namespace dpm
+
+

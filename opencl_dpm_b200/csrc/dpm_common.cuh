@@ -52,6 +52,9 @@ struct NbrBuffers {
   float *partial;  // [grid][16] block partials of the reduction
   int *chunk_sum;  // [grid]
   int nc;          // cells binned (owned + ghosts)
+  const int *nc_dev;  // if non-null the binned cell count is read from the device (sharded runs: owned + received ghosts)
+  const int *gid;     // if non-null, global cell ids: candidate lists are ordered by gid so that the force summation
+                      // order (and hence every bit of the result) is independent of the decomposition
   int nc_list;     // cells that get candidate lists (owned)
   int nd;
   int cap;

@@ -1,0 +1,341 @@
+// dpm_halo.cu — multi-GPU slab decomposition of the 3D path with a per-step halo exchange over NCCL.
+//
+// The reference is single-device; this is new work for BASELINE config E (262,144 cells at
+// 2/4/8 GPUs).  One process per GPU; rank r owns a slab of cells (ownership is static — any
+// assignment is correct, a spatially compact one keeps the halo small).  Shape forces, the substrate force and
+// the integration are per-cell; only the repulsion reads other cells' START-OF-STEP vertices, and it writes the
+// vertex's own force only (shaders/Cell3D_Kernel.cl:308), so ghosts are read-only and nothing flows back.
+//
+// Every step, on the compute stream, with NO host synchronisation:
+//   1. shard_prepare_kernel   region box + largest extent/contact pad of the owned cells, local rebuild flag
+//   2. ncclAllGather          8 floats per rank (the only collective; it also makes the rebuild decision global)
+//   3. shard_select_kernel    if any rank wants a rebuild: new send lists (owned cells whose padded box reaches a
+//                             peer's region), in ascending cell order
+//   4. shard_pack_kernel      gather {global id, bounds, nv float4 vertices} of the listed cells per peer
+//   5. ncclSend / ncclRecv    one fixed-capacity message per peer (ring of slabs: left and right neighbour)
+//   6. shard_unpack_kernel    ghosts appended behind the owned cells in pos/bnd/gid; total cell count on device
+// then the usual rebuild kernel (device-flag driven, now over owned + ghost cells) and the step kernel (owned).
+// Candidate lists are ordered by GLOBAL id, so forces are summed in the same order as on one GPU and a sharded
+// run reproduces the single-GPU run bit for bit (tests/test_gpu_multi.py).
+//
+// NCCL is resolved at run time (dlopen "libnccl.so.2"): a single-GPU user needs no NCCL at all, and inside a
+// torch process the already-loaded library is reused.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+#include <vector>
+
+#include "dpm3d_ctx.cuh"
+
+namespace dpm {
+
+constexpr int MAXR = 64;      // ranks
+constexpr int GATHER = 8;     // floats per rank in the all-gather
+constexpr int HDR_INTS = 16;  // message header
+
+struct ShardDev {
+  int n_total;  // owned + ghosts (MUST stay the first member: the rebuild kernel reads it as an int*)
+  int n_ghost;
+  int send_count[2];
+  int error;  // 1: a peer message overflowed the ghost capacity; 2: a cell reaches beyond the adjacent slabs
+  int rebuilds_global;
+  float margin;
+  int pad;
+};
+
+struct Nccl {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+  Nccl() {
+    const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int i = 0; names[i] && !lib; i++) lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return;
+#define SYM(m, n) m = reinterpret_cast<decltype(m)>(dlsym(lib, n))
+    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllGather, "ncclAllGather"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    ok = GetUniqueId && CommInitRank && AllGather && Send && Recv && GroupStart && GroupEnd;
+  }
+};
+static Nccl &nccl() {
+  static Nccl n;
+  return n;
+}
+#define DPM_NCCL_TRY(expr)                                                                                       \
+  do {                                                                                                           \
+    ncclResult_t _r = (expr);                                                                                    \
+    if (_r != ncclSuccess)                                                                                       \
+      return fail(DPM_ERR_NCCL, std::string(#expr) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(_r) : "nccl error")); \
+  } while (0)
+
+// message layout for capacity C cells and nv vertices per cell (all sections 16-byte aligned, C % 4 == 0)
+__host__ __device__ inline size_t msg_off_gid() { return sizeof(int) * HDR_INTS; }
+__host__ __device__ inline size_t msg_off_bnd(int C) { return msg_off_gid() + sizeof(int) * (size_t)C; }
+__host__ __device__ inline size_t msg_off_pos(int C) { return msg_off_bnd(C) + sizeof(float4) * 3 * (size_t)C; }
+__host__ __device__ inline size_t msg_size(int C, int nv) { return msg_off_pos(C) + sizeof(float4) * (size_t)nv * C; }
+
+// ---- 1. per-rank summary -------------------------------------------------------------------------------------
+__global__ void shard_prepare_kernel(const float4 *bnd, int n_own, const NbrState *st, float *out) {
+  __shared__ float s[8][4];
+  float rlo = INFINITY, rhi = -INFINITY, ext = 0.f, pad = 0.f;
+  for (int c = threadIdx.x; c < n_own; c += blockDim.x) {
+    const float4 lo = bnd[3 * (size_t)c], hi = bnd[3 * (size_t)c + 1];
+    rlo = fminf(rlo, lo.x); rhi = fmaxf(rhi, hi.x);
+    ext = fmaxf(ext, fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z)));
+    pad = fmaxf(pad, hi.w);
+  }
+  rlo = warp_min(rlo); rhi = warp_max(rhi); ext = warp_max(ext); pad = warp_max(pad);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { s[w][0] = rlo; s[w][1] = rhi; s[w][2] = ext; s[w][3] = pad; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)blockDim.x / 32; i++) {
+      s[0][0] = fminf(s[0][0], s[i][0]); s[0][1] = fmaxf(s[0][1], s[i][1]);
+      s[0][2] = fmaxf(s[0][2], s[i][2]); s[0][3] = fmaxf(s[0][3], s[i][3]);
+    }
+    out[0] = st->rebuild ? 1.f : 0.f;
+    out[1] = s[0][0]; out[2] = s[0][1]; out[3] = s[0][2]; out[4] = s[0][3];
+    out[5] = out[6] = out[7] = 0.f;
+  }
+}
+
+// does [lo-m, hi+m] reach region [qlo, qhi] under the periodic image that brings them closest?
+__device__ __forceinline__ bool reaches(float lo, float hi, float m, float qlo, float qhi, int pbc, float L) {
+  float d = 0.5f * (lo + hi) - 0.5f * (qlo + qhi);
+  if (pbc) d -= L * roundf(d / L);
+  return fabsf(d) <= 0.5f * (hi - lo) + m + 0.5f * (qhi - qlo);
+}
+
+// ---- 3. send lists (single CTA, deterministic ascending order) ---------------------------------------------------
+__global__ void shard_select_kernel(const float4 *bnd, int n_own, NbrState *st, ShardDev *sd, const float *all, int rank,
+                                    int nranks, int npeers, int peer0, int peer1, int *list0, int *list1, int cap,
+                                    float skin_rel, int pbc, float L) {
+  __shared__ int s_cnt[8][2];
+  __shared__ int s_base[2];
+  __shared__ int s_any;
+  bool any = false;
+  float ext = 0.f, pad = 0.f;
+  for (int r = 0; r < nranks; r++) {
+    any |= all[r * GATHER] != 0.f;
+    ext = fmaxf(ext, all[r * GATHER + 3]);
+    pad = fmaxf(pad, all[r * GATHER + 4]);
+  }
+  if (!any) return;  // uniform
+  // lists stay valid while every cell stays in its build box (skin/2 each) and pads stay below the build range
+  const float margin = skin_rel * ext + RANGE_HEADROOM * pad + 1e-4f * ext;
+  if (threadIdx.x == 0) { st->rebuild = 1; sd->margin = margin; sd->rebuilds_global += 1; s_base[0] = s_base[1] = 0; s_any = 0; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int peers[2] = {peer0, peer1};
+  for (int c0 = 0; c0 < n_own; c0 += blockDim.x) {
+    const int c = c0 + threadIdx.x;
+    bool want[2] = {false, false};
+    if (c < n_own) {
+      const float4 lo = bnd[3 * (size_t)c], hi = bnd[3 * (size_t)c + 1];
+      for (int p = 0; p < npeers; p++) want[p] = reaches(lo.x, hi.x, margin, all[peers[p] * GATHER + 1], all[peers[p] * GATHER + 2], pbc, L);
+      // a cell that reaches a slab which is not an adjacent one cannot be served by this ring exchange
+      for (int r = 0; r < nranks; r++)
+        if (r != rank && r != peer0 && r != peer1 && reaches(lo.x, hi.x, margin, all[r * GATHER + 1], all[r * GATHER + 2], pbc, L)) s_any = 1;
+    }
+    unsigned b[2];
+    for (int p = 0; p < 2; p++) { b[p] = __ballot_sync(0xffffffffu, want[p]); if (lane == 0) s_cnt[w][p] = __popc(b[p]); }
+    __syncthreads();
+    for (int p = 0; p < npeers; p++) {
+      int off = s_base[p];
+      for (int i = 0; i < w; i++) off += s_cnt[i][p];
+      if (want[p]) {
+        const int pos = off + __popc(b[p] & ((1u << lane) - 1u));
+        if (pos < cap) (p == 0 ? list0 : list1)[pos] = c;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int p = 0; p < 2; p++) { int t = 0; for (int i = 0; i < nw; i++) t += s_cnt[i][p]; s_base[p] += t; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    for (int p = 0; p < 2; p++) { sd->send_count[p] = min(s_base[p], cap); if (s_base[p] > cap) sd->error = 1; }
+    if (s_any) sd->error = 2;
+  }
+}
+
+// ---- 4. pack: one CTA per (peer, slot) ----------------------------------------------------------------------------
+__global__ void shard_pack_kernel(const float4 *pos, const float4 *bnd, const int *gid, const ShardDev *sd, const int *list0,
+                                  const int *list1, unsigned char *buf0, unsigned char *buf1, int cap, int nv) {
+  const int p = blockIdx.x / cap, s = blockIdx.x % cap;
+  unsigned char *buf = p == 0 ? buf0 : buf1;
+  const int cnt = sd->send_count[p];
+  if (s == 0 && threadIdx.x < HDR_INTS) reinterpret_cast<int *>(buf)[threadIdx.x] = threadIdx.x == 0 ? cnt : 0;
+  if (s >= cnt) return;
+  const int c = (p == 0 ? list0 : list1)[s];
+  if (threadIdx.x == 0) reinterpret_cast<int *>(buf + msg_off_gid())[s] = gid[c];
+  if (threadIdx.x < 3) reinterpret_cast<float4 *>(buf + msg_off_bnd(cap))[3 * s + threadIdx.x] = bnd[3 * (size_t)c + threadIdx.x];
+  float4 *dst = reinterpret_cast<float4 *>(buf + msg_off_pos(cap)) + (size_t)s * nv;
+  const float4 *src = pos + (size_t)c * nv;
+  for (int v = threadIdx.x; v < nv; v += blockDim.x) dst[v] = src[v];
+}
+
+// ---- 6. unpack: ghosts appended behind the owned cells -----------------------------------------------------------
+__global__ void shard_unpack_kernel(float4 *pos, float4 *bnd, int *gid, ShardDev *sd, const unsigned char *buf0,
+                                    const unsigned char *buf1, int npeers, int n_own, int cap, int nv) {
+  const int p = blockIdx.x / cap, s = blockIdx.x % cap;
+  const int cnt0 = min(reinterpret_cast<const int *>(buf0)[0], cap);
+  const int cnt1 = npeers > 1 ? min(reinterpret_cast<const int *>(buf1)[0], cap) : 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { sd->n_ghost = cnt0 + cnt1; sd->n_total = n_own + cnt0 + cnt1; }
+  const int cnt = p == 0 ? cnt0 : cnt1;
+  if (s >= cnt) return;
+  const unsigned char *buf = p == 0 ? buf0 : buf1;
+  const int c = n_own + (p == 0 ? 0 : cnt0) + s;
+  if (threadIdx.x == 0) gid[c] = reinterpret_cast<const int *>(buf + msg_off_gid())[s];
+  if (threadIdx.x < 3) bnd[3 * (size_t)c + threadIdx.x] = reinterpret_cast<const float4 *>(buf + msg_off_bnd(cap))[3 * s + threadIdx.x];
+  const float4 *src = reinterpret_cast<const float4 *>(buf + msg_off_pos(cap)) + (size_t)s * nv;
+  float4 *dst = pos + (size_t)c * nv;
+  for (int v = threadIdx.x; v < nv; v += blockDim.x) dst[v] = src[v];
+}
+
+__global__ void iota_kernel(int *a, int n, int base) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = base + i;
+}
+
+int shard_exchange(dpm3d_ctx *h, int pbc, float L) {
+  Nccl &N = nccl();
+  ncclComm_t comm = static_cast<ncclComm_t>(h->comm);
+  float4 *pos = h->pos[h->cur], *bnd = h->bnd[h->cur];
+  shard_prepare_kernel<<<1, 256, 0, h->stream>>>(bnd, h->nc, h->st, h->gather_send);
+  DPM_NCCL_TRY(N.AllGather(h->gather_send, h->gather_all, GATHER, ncclFloat, comm, h->stream));
+  shard_select_kernel<<<1, 256, 0, h->stream>>>(bnd, h->nc, h->st, h->sd, h->gather_all, h->rank, h->nranks, h->npeers, h->peer[0],
+                                                 h->npeers > 1 ? h->peer[1] : -1, h->sendlist[0], h->sendlist[1], h->ghost_cap,
+                                                 h->skin_rel, pbc, L);
+  shard_pack_kernel<<<h->ghost_cap * h->npeers, 128, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->sendlist[0], h->sendlist[1],
+                                                                      h->sendbuf[0], h->sendbuf[1], h->ghost_cap, h->nv);
+  DPM_CUDA_TRY(cudaGetLastError());
+  DPM_NCCL_TRY(N.GroupStart());
+  for (int p = 0; p < h->npeers; p++) {
+    DPM_NCCL_TRY(N.Send(h->sendbuf[p], h->msg_bytes, ncclChar, h->peer[p], comm, h->stream));
+    DPM_NCCL_TRY(N.Recv(h->recvbuf[p], h->msg_bytes, ncclChar, h->peer[p], comm, h->stream));
+  }
+  DPM_NCCL_TRY(N.GroupEnd());
+  shard_unpack_kernel<<<h->ghost_cap * h->npeers, 128, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->recvbuf[0], h->recvbuf[1], h->npeers,
+                                                                        h->nc, h->ghost_cap, h->nv);
+  DPM_CUDA_TRY(cudaGetLastError());
+  h->stats.launches += 4;
+  h->stats.halo_bytes += (uint64_t)h->msg_bytes * h->npeers;
+  return DPM_OK;
+}
+
+int shard_check(dpm3d_ctx *h) {
+  ShardDev sd;
+  DPM_CUDA_TRY(cudaMemcpyAsync(&sd, h->sd, sizeof(ShardDev), cudaMemcpyDeviceToHost, h->stream));
+  DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (sd.error == 1) return fail(DPM_ERR_RUNTIME, "halo overflow: more boundary cells than max_ghost per neighbouring slab");
+  if (sd.error == 2) return fail(DPM_ERR_RUNTIME, "slab decomposition too thin: a cell interacts beyond the adjacent slabs");
+  return DPM_OK;
+}
+
+void shard_free(dpm3d_ctx *h) {
+  void *ptrs[] = {h->gid, h->sd, h->gather_send, h->gather_all, h->sendbuf[0], h->sendbuf[1], h->recvbuf[0], h->recvbuf[1],
+                  h->sendlist[0], h->sendlist[1]};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  h->gid = nullptr; h->sd = nullptr;
+  if (h->comm && nccl().CommDestroy) nccl().CommDestroy(static_cast<ncclComm_t>(h->comm));
+  h->comm = nullptr;
+}
+
+}  // namespace dpm
+
+using namespace dpm;
+
+extern "C" {
+
+int dpm_nccl_unique_id(uint8_t id[128]) {
+  if (!id) return fail(DPM_ERR_INVALID_ARGUMENT, "id is NULL");
+  if (!nccl().ok) return fail(DPM_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  ncclUniqueId u;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  DPM_NCCL_TRY(nccl().GetUniqueId(&u));
+  memcpy(id, &u, 128);
+  return DPM_OK;
+}
+
+// Turns a freshly created handle (ncells = cells OWNED by this rank) into one shard of a slab-decomposed tissue.
+// Must be called before the first upload.  max_ghost = ghost cells accepted from EACH neighbouring slab.
+int dpm3d_shard_init(dpm3d_t *h, int rank, int nranks, const uint8_t id[128], int max_ghost) {
+  if (!h || !id) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (nranks < 2 || nranks > MAXR || rank < 0 || rank >= nranks || max_ghost < 4)
+    return fail(DPM_ERR_INVALID_ARGUMENT, "need 2 <= nranks <= 64, 0 <= rank < nranks, max_ghost >= 4");
+  if (h->uploaded || h->nranks > 1) return fail(DPM_ERR_INVALID_ARGUMENT, "dpm3d_shard_init must be the first call on a fresh handle");
+  if (!nccl().ok) return fail(DPM_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(h->device);
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev};
+  max_ghost = (max_ghost + 3) & ~3;
+  h->rank = rank; h->nranks = nranks; h->ghost_cap = max_ghost;
+  const int left = (rank + nranks - 1) % nranks, right = (rank + 1) % nranks;
+  h->npeers = (left == right) ? 1 : 2;
+  h->peer[0] = left; h->peer[1] = right;
+  h->nslots = h->nc + h->npeers * max_ghost;
+  // regrow every per-cell array that also holds ghosts
+  const size_t nvert = (size_t)h->nslots * h->nv;
+  void **grow[] = {(void **)&h->pos[0], (void **)&h->pos[1], (void **)&h->bnd[0], (void **)&h->bnd[1], (void **)&h->bbox_lo,
+                   (void **)&h->bbox_hi, (void **)&h->bin_id, (void **)&h->order, (void **)&h->bin_count, (void **)&h->bin_start};
+  h->cap = 4 * h->nslots + 1024;
+  const size_t sizes[] = {sizeof(float4) * nvert, sizeof(float4) * nvert, sizeof(float4) * 3 * h->nslots, sizeof(float4) * 3 * h->nslots,
+                          sizeof(float4) * h->nslots, sizeof(float4) * h->nslots, sizeof(int) * h->nslots, sizeof(int) * h->nslots,
+                          sizeof(int) * (h->cap + 1), sizeof(int) * (h->cap + 1)};
+  for (int i = 0; i < 10; i++) {
+    if (*grow[i]) cudaFree(*grow[i]);
+    *grow[i] = nullptr;
+    DPM_CUDA_TRY(cudaMalloc(grow[i], sizes[i]));
+    DPM_CUDA_TRY(cudaMemset(*grow[i], 0, sizes[i]));
+  }
+  h->msg_bytes = msg_size(max_ghost, h->nv);
+  DPM_CUDA_TRY(cudaMalloc(&h->gid, sizeof(int) * h->nslots));
+  iota_kernel<<<(h->nslots + 255) / 256, 256>>>(h->gid, h->nslots, 0);
+  DPM_CUDA_TRY(cudaMalloc(&h->sd, sizeof(ShardDev)));
+  DPM_CUDA_TRY(cudaMemset(h->sd, 0, sizeof(ShardDev)));
+  DPM_CUDA_TRY(cudaMalloc(&h->gather_send, sizeof(float) * GATHER));
+  DPM_CUDA_TRY(cudaMalloc(&h->gather_all, sizeof(float) * GATHER * nranks));
+  for (int p = 0; p < h->npeers; p++) {
+    DPM_CUDA_TRY(cudaMalloc(&h->sendbuf[p], h->msg_bytes));
+    DPM_CUDA_TRY(cudaMalloc(&h->recvbuf[p], h->msg_bytes));
+    DPM_CUDA_TRY(cudaMemset(h->sendbuf[p], 0, h->msg_bytes));
+    DPM_CUDA_TRY(cudaMemset(h->recvbuf[p], 0, h->msg_bytes));
+    DPM_CUDA_TRY(cudaMalloc(&h->sendlist[p], sizeof(int) * max_ghost));
+  }
+  DPM_CUDA_TRY(cudaDeviceSynchronize());
+  ncclUniqueId u;
+  memcpy(&u, id, 128);
+  ncclComm_t comm = nullptr;
+  DPM_NCCL_TRY(nccl().CommInitRank(&comm, nranks, u, rank));
+  h->comm = comm;
+  return DPM_OK;
+}
+
+// Global ids of the OWNED cells (length ncells).  Candidate lists are ordered by global id, which makes a sharded
+// run sum forces in exactly the single-GPU order.
+int dpm3d_set_global_ids(dpm3d_t *h, const int32_t *gid) {
+  if (!h || !gid) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (h->nranks < 2) return fail(DPM_ERR_INVALID_ARGUMENT, "dpm3d_set_global_ids needs a sharded handle (dpm3d_shard_init)");
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(h->device);
+  cudaError_t e = cudaMemcpy(h->gid, gid, sizeof(int) * h->nc, cudaMemcpyHostToDevice);
+  if (prev >= 0) cudaSetDevice(prev);
+  if (e != cudaSuccess) return fail(DPM_ERR_CUDA, cudaGetErrorString(e));
+  return DPM_OK;
+}
+
+}  // extern "C"

@@ -101,6 +101,7 @@ __device__ __forceinline__ bool axis_far(float li, float hi, float lj, float hj,
 
 __global__ void __launch_bounds__(RB_THREADS) nbr_rebuild_kernel(NbrBuffers nb) {
   if (nb.st->rebuild == 0) return;  // uniform across the grid: nobody reaches a grid sync
+  if (nb.nc_dev) nb.nc = *nb.nc_dev;
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   const int gtid = blockIdx.x * blockDim.x + tid;
@@ -299,9 +300,10 @@ __global__ void __launch_bounds__(RB_THREADS) nbr_rebuild_kernel(NbrBuffers nb) 
       }
     }
     int m = min(n, KMAX);
-    for (int a = 1; a < m; a++) {
-      int v = tmp[a], q = a - 1;
-      while (q >= 0 && tmp[q] > v) { tmp[q + 1] = tmp[q]; q--; }
+    for (int a = 1; a < m; a++) {  // ascending (global) cell id == the reference's cj loop order
+      const int v = tmp[a], kv = nb.gid ? nb.gid[v] : v;
+      int q = a - 1;
+      while (q >= 0 && (nb.gid ? nb.gid[tmp[q]] : tmp[q]) > kv) { tmp[q + 1] = tmp[q]; q--; }
       tmp[q + 1] = v;
     }
     nb.cand_count[i] = n;
