@@ -41,10 +41,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_workload(name: str, rank: int = 0):
-    from opencl_dpm_b200 import synth
+def make_workload(name: str, rank: int = 0, world: int = 1):
+    from opencl_dpm_b200 import shard, synth
 
-    if name == "D642":
+    if name in ("E642", "E162"):
+        # BASELINE config E: 512 x 512 = 262,144 cells; each rank builds only its x-slab of lattice columns
+        sub = 3 if name == "E642" else 2
+        i0, i1 = shard.slab_columns(512, rank, world)
+        d = synth.monolayer3d(512, subdiv=sub, x_range=(i0, i1))
+        d["nc_global"] = 512 * 512
+        desc = (f"3D DPM 262,144-cell monolayer, {d['nv']}-vertex icospheres ({512 * 512 * d['nv']:,} vertices), x-slab decomposed over "
+                f"{world} GPU(s) with per-step NCCL halo exchange")
+    elif name == "D642":
         d = synth.monolayer3d(64, subdiv=3)
         desc = "3D DPM 4096-cell monolayer, 642-vertex icospheres (2,629,632 vertices), winding-number repulsion, substrate, PBC"
     elif name == "D162":
@@ -59,6 +67,7 @@ def make_workload(name: str, rank: int = 0):
     else:
         raise SystemExit(f"unknown workload {name}")
     d["name"], d["desc"], d["dim"] = name, desc, (2 if name == "B2D" else 3)
+    d.setdefault("nc_global", d["nc"])
     return d
 
 
@@ -151,11 +160,19 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="D642")
-    ap.add_argument("--inner", type=int, default=20, help="timesteps per bench step (one CLEulerUpdate call)")
+    ap.add_argument("--workload", default=None, help="D642 (default at 1 GPU), D162, C162, B2D, E642 (default at >1 GPU), E162")
+    ap.add_argument("--inner", type=int, default=None, help="timesteps per bench step (one CLEulerUpdate call)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload is None:
+        # 1 GPU: BASELINE config D (4096 cells, the north-star roofline target).  N > 1: config E (262,144 cells) is
+        # strong-scaled over the ranks; vertex-steps/s of this path is independent of the cell count (same lattice,
+        # same per-cell work), so the N=1 D642 value is the single-GPU baseline of the same metric.
+        args.workload = "D642" if world_env == 1 else "E642"
+    if args.inner is None:
+        args.inner = 20 if not args.workload.startswith("E") else 10
 
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -175,8 +192,9 @@ def main():
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     capi.lib()
-    d = make_workload(args.workload, rank)
+    d = make_workload(args.workload, rank, world)
     dim = d["dim"]
+    sharded = world > 1 and args.workload.startswith("E")
     stream = torch.cuda.Stream()  # a real (non-legacy) stream: the library launches on it and the events are recorded on it
     torch.cuda.set_stream(stream)
     nvert = d["nc"] * d["nv"] if dim == 3 else int(d["nv"].sum())
@@ -184,6 +202,11 @@ def main():
 
     if dim == 3:
         h = Dpm3D(d["nc"], d["nv"], d["faces"], device=local)
+        if sharded:
+            from opencl_dpm_b200 import shard
+
+            h.shard_init(rank, world, shard.broadcast_unique_id(rank), max_ghost=2 * 512)
+            h.set_global_ids(d["gid"])
         h.set_stream(stream.cuda_stream)
         params = [d[k] for k in PK3]
         dev_verts = torch.from_numpy(d["verts"]).cuda()
@@ -265,7 +288,13 @@ def main():
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    total_vs = nvert * args.inner * args.steps * world
+    if world > 1:
+        tv = torch.tensor([float(nvert)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tv, op=dist.ReduceOp.SUM)
+        nvert_all = int(tv.item())  # all ranks' owned vertices (sharded: the whole tissue; replicas: world copies)
+    else:
+        nvert_all = nvert
+    total_vs = nvert_all * args.inner * args.steps
     value = total_vs / (ms * 1e-3)
 
     # ---- end-to-end through the one-call seam with pinned host buffers (`e2e`) ---------------
@@ -279,19 +308,23 @@ def main():
         t = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_t = float(t.item())
-    e2e_value = nvert * args.inner * args.steps * world / e2e_t
+    e2e_value = nvert_all * args.inner * args.steps / e2e_t
 
     if rank == 0:
         peak, peak_src = peaks()
         n_step_kernels = args.inner * args.steps
         t_launch = ms * 1e-3 / n_step_kernels  # step-kernel launches dominate the region (the rebuild kernel is a no-op launch)
-        achieved = nvert * balg / t_launch / 1e9
+        achieved = nvert * balg / t_launch / 1e9  # per GPU: this rank's owned vertices per launch
         out = {
             "metric": "vertex-steps/sec (force+integrate)", "value": value, "unit": "vertex-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": d["desc"], "name": d["name"], "timesteps_per_step": args.inner, "dt": float(d["dt"]),
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one tissue per GPU)",
+                       "parallelism": ("single GPU" if world == 1 else
+                                       f"x-slab decomposition over {world} GPUs, ghost cells exchanged every timestep with ncclSend/ncclRecv "
+                                       f"(ring of slabs), one 8-float ncclAllGather per step for the global rebuild decision" if sharded
+                                       else f"{world} independent replicas (one tissue per GPU)"),
+                       "cells_per_gpu": int(d["nc"]), "cells_total": int(d["nc_global"]) if sharded or world == 1 else int(d["nc"]) * world,
                        "l2": "L2 flushed (256 MiB write) between timed steps; within a step consecutive timesteps reuse L2 as in the real loop",
                        "ms_per_timestep": ms / n_step_kernels},
             "clocks": clocks,
@@ -302,9 +335,9 @@ def main():
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "algorithmic_bytes_per_vertex_step": balg, "us_per_launch": t_launch * 1e6},
             "stats": {"rebuilds": int(st.rebuilds), "contact_evals_per_timestep": st.contact_evals / max(1, st.steps),
-                      "wall_s_timed_region": t_wall},
+                      "wall_s_timed_region": t_wall, "halo_bytes_per_timestep_rank0": st.halo_bytes / max(1, st.steps)},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline_sample(d)
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -65,6 +65,69 @@ int build_rings(int nv, int nf, const uint32_t *faces, std::vector<uint16_t> &ri
   return DPM_OK;
 }
 
+// Static tables of the fast contact evaluation: the face across each edge, and for every face the faces of its
+// edge-adjacency rings 0..RING_MAX in BFS order with the cumulative ring ends.
+void build_face_tables(int nf, const uint32_t *faces, std::vector<ushort4> &adj, std::vector<uint16_t> &ring_tab,
+                       std::vector<uint8_t> &ring_end) {
+  std::map<std::pair<uint32_t, uint32_t>, int> edge;
+  for (int f = 0; f < nf; f++)
+    for (int k = 0; k < 3; k++) edge[{faces[3 * f + k], faces[3 * f + (k + 1) % 3]}] = f;
+  adj.resize(nf);
+  for (int f = 0; f < nf; f++) {
+    unsigned short a[3];
+    for (int k = 0; k < 3; k++) a[k] = (unsigned short)edge[{faces[3 * f + (k + 1) % 3], faces[3 * f + k]}];  // closed manifold: exists
+    adj[f] = make_ushort4(a[0], a[1], a[2], 0);
+  }
+  ring_tab.assign((size_t)nf * RING_TAB, 0);
+  ring_end.assign((size_t)nf * (RING_MAX + 1), 0);
+  std::vector<int> mark(nf, -1);
+  for (int f = 0; f < nf; f++) {
+    std::vector<int> frontier{f}, order{f};
+    mark[f] = f;
+    ring_end[(size_t)f * (RING_MAX + 1)] = 1;
+    for (int r = 1; r <= RING_MAX; r++) {
+      std::vector<int> next;
+      for (int g : frontier) {
+        const unsigned short nb[3] = {adj[g].x, adj[g].y, adj[g].z};
+        for (int k = 0; k < 3; k++)
+          if (mark[nb[k]] != f && (int)order.size() < RING_TAB) { mark[nb[k]] = f; next.push_back(nb[k]); order.push_back(nb[k]); }
+      }
+      ring_end[(size_t)f * (RING_MAX + 1) + r] = (uint8_t)order.size();
+      frontier.swap(next);
+    }
+    for (size_t j = 0; j < order.size(); j++) ring_tab[(size_t)f * RING_TAB + j] = (uint16_t)order[j];
+  }
+}
+
+// Walk-start guess: octahedral direction map -> face of cell 0 (about its centroid) containing that direction.
+void build_dir_table(int nv, int nf, const uint32_t *faces, const float *verts4_cell0, std::vector<uint16_t> &tab) {
+  double c[3] = {0, 0, 0};
+  for (int v = 0; v < nv; v++) for (int d = 0; d < 3; d++) c[d] += verts4_cell0[4 * v + d];
+  for (int d = 0; d < 3; d++) c[d] /= nv;
+  tab.assign(DIR_N * DIR_N, 0);
+  for (int iy = 0; iy < DIR_N; iy++)
+    for (int ix = 0; ix < DIR_N; ix++) {
+      double x = (ix + 0.5) / DIR_N * 2 - 1, y = (iy + 0.5) / DIR_N * 2 - 1, z = 1 - std::fabs(x) - std::fabs(y);
+      if (z < 0) { const double tx = (1 - std::fabs(y)) * (x >= 0 ? 1 : -1), ty = (1 - std::fabs(x)) * (y >= 0 ? 1 : -1); x = tx; y = ty; }
+      const double u[3] = {x, y, z};
+      int best = 0;
+      double bestv = -1e300;
+      for (int f = 0; f < nf; f++) {
+        double P[3][3];
+        for (int k = 0; k < 3; k++) for (int d = 0; d < 3; d++) P[k][d] = verts4_cell0[4 * faces[3 * f + k] + d] - c[d];
+        double m = 1e300;
+        for (int k = 0; k < 3; k++) {
+          const double *A = P[k], *B = P[(k + 1) % 3];
+          const double cr[3] = {A[1] * B[2] - A[2] * B[1], A[2] * B[0] - A[0] * B[2], A[0] * B[1] - A[1] * B[0]};
+          const double nrm = std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]) + 1e-300;
+          m = std::min(m, (u[0] * cr[0] + u[1] * cr[1] + u[2] * cr[2]) / nrm);
+        }
+        if (m > bestv) { bestv = m; best = f; }
+      }
+      tab[octa_texel((float)u[0], (float)u[1], (float)u[2])] = (uint16_t)best;
+    }
+}
+
 template <int T, int V>
 cudaError_t launch_step_t(const Step3DParams &p, size_t smem, cudaStream_t s) {
   dpm3d_step_kernel<T, V><<<p.nc, T, smem, s>>>(p);
@@ -112,7 +175,7 @@ NbrBuffers nbr_buffers(dpm3d_ctx *h, int pbc, float L) {
   nb.st = h->st;
   nb.blo = h->bnd[h->cur];
   nb.bhi = h->bnd[h->cur] + 1;
-  nb.blo_stride = 3;
+  nb.blo_stride = BND;
   nb.bbox_lo = h->bbox_lo; nb.bbox_hi = h->bbox_hi;
   nb.bin_id = h->bin_id; nb.order = h->order; nb.bin_count = h->bin_count; nb.bin_start = h->bin_start;
   nb.cand_count = h->cand_count; nb.cand = h->cand;
@@ -171,8 +234,8 @@ int dpm3d_create(dpm3d_t **out, int device, int ncells, int nv, int nf, const ui
   TRYB(cudaMalloc(&h->pos[1], sizeof(float4) * nvert));
   TRYB(cudaMalloc(&h->force, sizeof(float4) * nvert));
   TRYB(cudaMemsetAsync(h->force, 0, sizeof(float4) * nvert, h->stream));
-  TRYB(cudaMalloc(&h->bnd[0], sizeof(float4) * 3 * ncells));
-  TRYB(cudaMalloc(&h->bnd[1], sizeof(float4) * 3 * ncells));
+  TRYB(cudaMalloc(&h->bnd[0], sizeof(float4) * BND * ncells));
+  TRYB(cudaMalloc(&h->bnd[1], sizeof(float4) * BND * ncells));
   TRYB(cudaMalloc(&h->cellA, sizeof(float4) * ncells));
   TRYB(cudaMalloc(&h->cellB, sizeof(float4) * ncells));
   TRYB(cudaMallocHost(&h->h_cell, sizeof(float4) * 2 * ncells));
@@ -187,6 +250,19 @@ int dpm3d_create(dpm3d_t **out, int device, int ncells, int nv, int nf, const ui
     TRYB(cudaMemcpy(h->ring_nbr, rn.data(), sizeof(uint16_t) * rn.size(), cudaMemcpyHostToDevice));
     TRYB(cudaMemcpy(h->ring_face, rf.data(), sizeof(uint16_t) * rf.size(), cudaMemcpyHostToDevice));
     TRYB(cudaMemcpy(h->valence, val.data(), nv, cudaMemcpyHostToDevice));
+    std::vector<ushort4> adj;
+    std::vector<uint16_t> rtab;
+    std::vector<uint8_t> rend;
+    build_face_tables(nf, faces, adj, rtab, rend);
+    TRYB(cudaMalloc(&h->face_adj, sizeof(ushort4) * nf));
+    TRYB(cudaMalloc(&h->ring_tab, sizeof(uint16_t) * rtab.size()));
+    TRYB(cudaMalloc(&h->ring_end, rend.size()));
+    TRYB(cudaMalloc(&h->dir_table, sizeof(uint16_t) * DIR_N * DIR_N));
+    TRYB(cudaMemcpy(h->face_adj, adj.data(), sizeof(ushort4) * nf, cudaMemcpyHostToDevice));
+    TRYB(cudaMemcpy(h->ring_tab, rtab.data(), sizeof(uint16_t) * rtab.size(), cudaMemcpyHostToDevice));
+    TRYB(cudaMemcpy(h->ring_end, rend.data(), rend.size(), cudaMemcpyHostToDevice));
+    TRYB(cudaMemset(h->dir_table, 0, sizeof(uint16_t) * DIR_N * DIR_N));
+    h->h_faces.assign(faces, faces + 3 * (size_t)nf);
   }
   h->cap = 4 * ncells + 1024;
   TRYB(cudaMalloc(&h->st, sizeof(NbrState)));
@@ -216,7 +292,7 @@ int dpm3d_destroy(dpm3d_t *h) {
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   shard_free(h);
   void *ptrs[] = {h->pos[0], h->pos[1], h->force, h->bnd[0], h->bnd[1], h->cellA, h->cellB, h->faces, h->ring_nbr, h->ring_face,
-                  h->valence, h->st, h->bbox_lo, h->bbox_hi, h->bin_id, h->order, h->bin_count, h->bin_start, h->cand_count,
+                  h->valence, h->face_adj, h->ring_tab, h->ring_end, h->dir_table, h->st, h->bbox_lo, h->bbox_hi, h->bin_id, h->order, h->bin_count, h->bin_start, h->cand_count,
                   h->cand, h->partial, h->chunk_sum};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (h->h_cell) cudaFreeHost(h->h_cell);
@@ -274,8 +350,17 @@ static int upload_common(dpm3d_t *h, const float *verts4, bool on_device, const 
   DPM_CUDA_TRY(cudaMemcpyAsync(h->cellA, h->h_cell, sizeof(float4) * h->nc, cudaMemcpyHostToDevice, h->stream));
   DPM_CUDA_TRY(cudaMemcpyAsync(h->cellB, h->h_cell + h->nc, sizeof(float4) * h->nc, cudaMemcpyHostToDevice, h->stream));
   DPM_CUDA_TRY(cudaMemsetAsync(h->st, 0, sizeof(NbrState), h->stream));
+  {  // walk-start table of the fast contact evaluation, from cell 0's current shape
+    std::vector<float> cell0(4 * (size_t)h->nv);
+    if (on_device) DPM_CUDA_TRY(cudaMemcpy(cell0.data(), verts4, sizeof(float) * cell0.size(), cudaMemcpyDeviceToHost));
+    else memcpy(cell0.data(), verts4, sizeof(float) * cell0.size());
+    std::vector<uint16_t> tab;
+    build_dir_table(h->nv, h->nf, h->h_faces.data(), cell0.data(), tab);
+    DPM_CUDA_TRY(cudaMemcpyAsync(h->dir_table, tab.data(), sizeof(uint16_t) * tab.size(), cudaMemcpyHostToDevice, h->stream));
+    DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
   dpm3d_bounds_kernel<<<h->nc, 128, sizeof(float4) * h->nv, h->stream>>>(h->pos[0], h->bnd[0], h->nc, h->nv, h->ring_nbr,
-                                                                          h->valence, h->ring_stride);
+                                                                          h->valence, h->ring_stride, h->faces, h->nf);
   DPM_CUDA_TRY(cudaGetLastError());
   h->stats.launches += 1;
   h->stats.steps = 0; h->stats.rebuilds = 0; h->stats.contact_evals = 0;  // per-upload counters (launches stay cumulative)
@@ -318,6 +403,7 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
   Step3DParams p{};
   p.cellA = h->cellA; p.cellB = h->cellB; p.faces = h->faces;
   p.ring_nbr = h->ring_nbr; p.ring_face = h->ring_face; p.valence = h->valence; p.ring_stride = h->ring_stride;
+  p.face_adj = h->face_adj; p.ring_tab = h->ring_tab; p.ring_end = h->ring_end; p.dir_table = h->dir_table;
   p.cand_count = h->cand_count; p.cand = h->cand; p.K = h->K;
   p.bbox_lo = h->bbox_lo; p.bbox_hi = h->bbox_hi; p.st = h->st;
   p.nc = h->nc; p.nv = h->nv; p.nf = h->nf; p.dt = dt; p.Kc = Kre; p.pbc = pbc; p.L = L; p.mask = h->mask;
@@ -350,6 +436,9 @@ static int check_device_flags(dpm3d_t *h) {
   DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->stats.rebuilds = (uint64_t)st.nbuilds;
   h->stats.contact_evals = st.contact_evals;
+  h->stats.reserved[0] = st.literal_evals;
+  h->stats.reserved[1] = st.fallback_why[0] | (st.fallback_why[1] << 32);  // diagnostics: not-star | near-COM
+  h->stats.reserved[2] = st.fallback_why[2] | (st.fallback_why[3] << 32);  //              walk limit | ring limit
   if (st.overflow) return fail(DPM_ERR_RUNTIME, "neighbour candidate list overflow: raise max_candidates (dpm3d_set_neighbor_params)");
   if (h->nranks > 1) return shard_check(h);
   return DPM_OK;
@@ -423,8 +512,10 @@ int dpm3d_get_neighbor_artifacts(dpm3d_t *h, dpm_grid_t *grid, int32_t *bin_id, 
 int dpm3d_get_cell_bounds(dpm3d_t *h, float *bounds12) {
   if (!h || !h->uploaded || !bounds12) return fail(DPM_ERR_INVALID_ARGUMENT, "no state");
   DeviceGuard guard(h->device);
-  DPM_CUDA_TRY(cudaMemcpyAsync(bounds12, h->bnd[h->cur], sizeof(float4) * 3 * h->nc, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<float> tmp((size_t)4 * BND * h->nc);
+  DPM_CUDA_TRY(cudaMemcpyAsync(tmp.data(), h->bnd[h->cur], sizeof(float4) * BND * h->nc, cudaMemcpyDeviceToHost, h->stream));
   DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < h->nc; c++) memcpy(bounds12 + 12 * (size_t)c, tmp.data() + 4 * BND * (size_t)c, sizeof(float) * 12);
   return DPM_OK;
 }
 

@@ -1,5 +1,7 @@
 // dpm3d_ctx.cuh — the 3D handle, shared by dpm3d.cu (single-GPU path) and dpm_halo.cu (slab sharding).
 #pragma once
+#include <vector>
+
 #include "dpm3d_kernels.cuh"
 
 namespace dpm {
@@ -20,6 +22,11 @@ struct dpm3d_ctx {
   uint16_t *ring_nbr = nullptr, *ring_face = nullptr;
   uint8_t *valence = nullptr;
   int ring_stride = 0;
+  ushort4 *face_adj = nullptr;     // static topology tables of the fast contact evaluation (dpm3d_kernels.cuh)
+  uint16_t *ring_tab = nullptr;
+  uint8_t *ring_end = nullptr;
+  uint16_t *dir_table = nullptr;   // rebuilt at every upload from cell 0
+  std::vector<uint32_t> h_faces;
   // neighbour search
   NbrState *st = nullptr;
   float4 *bbox_lo = nullptr, *bbox_hi = nullptr;

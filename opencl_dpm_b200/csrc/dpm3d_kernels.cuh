@@ -37,6 +37,10 @@ struct Step3DParams {
   const uint16_t *__restrict__ ring_face;
   const uint8_t *__restrict__ valence;
   int ring_stride;
+  const ushort4 *__restrict__ face_adj;    // face across edge (a,b), (b,c), (c,a)
+  const uint16_t *__restrict__ ring_tab;   // per face: faces in BFS (edge-adjacency) order, RING_TAB entries
+  const uint8_t *__restrict__ ring_end;    // per face: cumulative end of rings 0..RING_MAX
+  const uint16_t *__restrict__ dir_table;  // octahedral direction map (DIR_N x DIR_N) -> face, walk start guess
   const int *__restrict__ cand_count;
   const int *__restrict__ cand;
   int K;
@@ -53,20 +57,34 @@ struct Step3DParams {
 };
 
 constexpr int UNIT_CAP_FACTOR = 2;  // unit list capacity = factor * THREADS
-// The reference skips faces with denom < 1e-8 (shaders/Cell3D_Kernel.cl:293-295): every face that subtends more
-// than pi steradians from the vertex.  Its winding number is therefore the true one (0 outside a closed mesh)
-// only if no face is that close.  Every point of a face lies within 2/3 of its longest median, hence within
-// (2/3) e of its centroid (e = longest edge); a ball of that radius subtends < pi steradians once the distance to
-// its centre exceeds (2/sqrt 3)(2/3) e = 0.7698 e.  Centroids lie inside the cell's bounding box/sphere, so a
-// vertex farther than CONTACT_PAD * emax from them gets exactly zero repulsion from that cell and is culled.
-constexpr float CONTACT_PAD = 0.775f;
+constexpr int BND = 4;              // float4 per cell in the bounds arrays:
+                                    //   (lo.xyz, r2max) (hi.xyz, contact pad) (com.xyz, volume) (r2min, star flag, 0, 0)
+// The reference skips faces with denom < 1e-8 (shaders/Cell3D_Kernel.cl:293-295), i.e. every face that subtends
+// at least pi steradians from the vertex, so its "winding number" is
+//        w_ref(p) = W(p) - (1/4pi) * sum over skipped faces of Omega_f(p),      W = true winding number (0 or 1).
+// A planar triangle subtends >= pi only if the vertex projects INSIDE it (otherwise it lies in an open half-plane
+// seen from the foot point, < pi) and its height h above the plane satisfies h <= R/sqrt(3) <= e/3, R <= e/sqrt(3)
+// being the radius of the triangle's enclosing circle and e its longest edge.  Hence a face can only be skipped if
+// some point of it is within e/3 of the vertex: a vertex farther than CONTACT_PAD * emax from a cell's bounding
+// box / sphere gets w_ref = W = 0 from it and is culled exactly.
+constexpr float CONTACT_PAD = 0.34f;
 constexpr float RANGE_HEADROOM = 1.25f;  // lists are built for pads up to 1.25x the largest current one
+constexpr int RING_MAX = 5;              // edge-adjacency rings examined around the radially hit face
+constexpr int RING_TAB = 48;             // 1 + 3 + 6 + 9 + 12 + 15 = 46 faces
+constexpr int DIR_N = 16;                // octahedral map resolution
+constexpr int MAX_WALK = 64;
+constexpr int UNIT_LANES = 8;            // lanes cooperating on one (vertex, neighbour) unit: ring faces / literal faces in parallel
+
+__device__ __forceinline__ float group_sum(float v, unsigned gmask) {
+#pragma unroll
+  for (int o = UNIT_LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
+}
 
 template <int THREADS>
 size_t step3d_smem_bytes(int nv, int nf, int K) {
   size_t b = 0;
   b += sizeof(float4) * nv;                      // sP
-  b += sizeof(float4) * nv * (THREADS / 32);     // sU (per-warp unit vectors)
   b += sizeof(float) * nf;                       // sTerm
   b += sizeof(float4) * K * 3;                   // per-candidate shift / lo / hi
   b += sizeof(float4) * K;                       // per-candidate sphere (com+shift, r2)
@@ -104,12 +122,162 @@ __device__ __forceinline__ float com_chain(const float4 *sP, int nv, int comp) {
   return __fmul_rn(s, __fdiv_rn(1.0f, (float)nv));
 }
 
+// octahedral direction -> texel of the DIR_N x DIR_N walk-start table (mirrored on the host in dpm3d.cu)
+__host__ __device__ inline int octa_texel(float x, float y, float z) {
+  const float s = fabsf(x) + fabsf(y) + fabsf(z);
+  float ox = x / s, oy = y / s;
+  if (z < 0.0f) {
+    const float tx = (1.0f - fabsf(oy)) * (ox >= 0.0f ? 1.0f : -1.0f), ty = (1.0f - fabsf(ox)) * (oy >= 0.0f ? 1.0f : -1.0f);
+    ox = tx; oy = ty;
+  }
+  int ix = (int)((ox * 0.5f + 0.5f) * DIR_N), iy = (int)((oy * 0.5f + 0.5f) * DIR_N);
+  ix = ix < 0 ? 0 : (ix > DIR_N - 1 ? DIR_N - 1 : ix);
+  iy = iy < 0 ? 0 : (iy > DIR_N - 1 ? DIR_N - 1 : iy);
+  return iy * DIR_N + ix;
+}
+
+// den / num of the reference's solid-angle formula for the face with corner vectors a, b, c = V + shift - p
+// (shaders/Cell3D_Kernel.cl:285-298); unit vectors by MUFU.RSQ + one Newton step.
+__device__ __forceinline__ void solid_angle_terms(float3 a, float3 b, float3 c, float &den, float &num) {
+  float da = dot3(a, a), db = dot3(b, b), dc = dot3(c, c);
+  float ra = rsqrtf(da), rb = rsqrtf(db), rc = rsqrtf(dc);
+  ra = ra * (1.5f - 0.5f * da * ra * ra);
+  rb = rb * (1.5f - 0.5f * db * rb * rb);
+  rc = rc * (1.5f - 0.5f * dc * rc * rc);
+  a = f3(a.x * ra, a.y * ra, a.z * ra); b = f3(b.x * rb, b.y * rb, b.z * rb); c = f3(c.x * rc, c.y * rc, c.z * rc);
+  den = 1.0f + dot3(a, b) + dot3(b, c) + dot3(c, a);
+  num = dot3(a, cross3(b, c));
+}
+
+// The reference's sum, literally, for one (vertex, neighbour) unit: every face, one lane.  Fallback of
+// winding_fast (neighbour not star-shaped about its COM, vertex within the pad of the COM, walk/ring limits).
+static __device__ __noinline__ float winding_literal(const float4 *__restrict__ Vj, const ushort4 *__restrict__ faces, int nf, float4 sh,
+                                              float4 p, int g, unsigned gmask) {
+  float om = 0.0f;
+  for (int f = g; f < nf; f += UNIT_LANES) {
+    const ushort4 fc = __ldg(faces + f);
+    const float4 q0 = __ldg(Vj + fc.x), q1 = __ldg(Vj + fc.y), q2 = __ldg(Vj + fc.z);
+    const float3 a = f3((q0.x + sh.x) - p.x, (q0.y + sh.y) - p.y, (q0.z + sh.z) - p.z);
+    const float3 b = f3((q1.x + sh.x) - p.x, (q1.y + sh.y) - p.y, (q1.z + sh.z) - p.z);
+    const float3 c = f3((q2.x + sh.x) - p.x, (q2.y + sh.y) - p.y, (q2.z + sh.z) - p.z);
+    float den, num;
+    solid_angle_terms(a, b, c, den, num);
+    if (!(den < 1e-8f)) om += 2.0f * atan2f(num, den);  // :293-299
+  }
+  return group_sum(om, gmask) / (4.0f * 3.14159274101257f);
+}
+
+// w_ref = W - (1/4pi) * sum_{faces with den < 1e-8} Omega_f, for a neighbour that is star-shaped about its COM C
+// (checked every step by the owner's epilogue):
+//   1. the face f* hit by the ray C -> p is found by walking the spherical triangulation seen from C, starting
+//      from a direction-table guess;  p is inside  <=>  p is on the inner side of f*'s plane   =>  W;
+//   2. a skipped face has a point within rho = pad of p (see CONTACT_PAD), hence intersects the cone of half-angle
+//      asin(rho / |p - C|) about the ray; faces meeting a cone form an edge-connected patch containing f*, so the
+//      rings of f* are examined outwards until a whole ring misses the (conservatively tested) cone;
+//   3. only those few faces get the reference's den / num / atan2.
+// Omega of a SKIPPED face (den < 1e-8) in double precision from the reference's fp32 corner vectors: for a vertex
+// nearly in the plane of a face that subtends ~pi both num and den are ~1e-3, and fp32 would lose 4 digits of
+// exactly the term that W - sum(...) needs (the literal sum never evaluates these faces, so it does not suffer).
+static __device__ __noinline__ float omega_skipped_f64(float3 a, float3 b, float3 c) {
+  const double ax = a.x, ay = a.y, az = a.z, bx = b.x, by = b.y, bz = b.z, cx = c.x, cy = c.y, cz = c.z;
+  const double la = sqrt(ax * ax + ay * ay + az * az), lb = sqrt(bx * bx + by * by + bz * bz), lc = sqrt(cx * cx + cy * cy + cz * cz);
+  const double num = ax * (by * cz - bz * cy) + ay * (bz * cx - bx * cz) + az * (bx * cy - by * cx);
+  const double den = la * lb * lc + (ax * bx + ay * by + az * bz) * lc + (bx * cx + by * cy + bz * cz) * la + (cx * ax + cy * ay + cz * az) * lb;
+  return (float)(2.0 * atan2(num, den));
+}
+
+// Returns 0 on success, else the reason the caller must fall back to the literal sum (1: vertex within the pad of
+// the neighbour's COM, 2: walk limit, 3: ring limit).
+__device__ __forceinline__ int winding_fast(const Step3DParams &P, const float4 *__restrict__ Vj, float4 sh, float4 p, float3 Cs,
+                                            float rho, float &w_out, int g, unsigned gmask) {
+  const float3 u = f3(p.x - Cs.x, p.y - Cs.y, p.z - Cs.z);
+  const float r2 = dot3(u, u);
+  if (!(r2 > 1.0201f * rho * rho)) return 1;
+  int f = __ldg(P.dir_table + octa_texel(u.x, u.y, u.z));
+  float3 A, B, C;
+  bool found = false;
+  for (int it = 0; it < MAX_WALK; it++) {
+    const ushort4 fc = __ldg(P.faces + f);
+    const float4 q0 = __ldg(Vj + fc.x), q1 = __ldg(Vj + fc.y), q2 = __ldg(Vj + fc.z);
+    A = f3((q0.x + sh.x) - Cs.x, (q0.y + sh.y) - Cs.y, (q0.z + sh.z) - Cs.z);
+    B = f3((q1.x + sh.x) - Cs.x, (q1.y + sh.y) - Cs.y, (q1.z + sh.z) - Cs.z);
+    C = f3((q2.x + sh.x) - Cs.x, (q2.y + sh.y) - Cs.y, (q2.z + sh.z) - Cs.z);
+    const float d0 = dot3(u, cross3(A, B)), d1 = dot3(u, cross3(B, C)), d2 = dot3(u, cross3(C, A));
+    const float dm = fminf(d0, fminf(d1, d2));
+    if (dm >= 0.0f) { found = true; break; }
+    const ushort4 ad = __ldg(P.face_adj + f);
+    f = (dm == d0) ? ad.x : (dm == d1 ? ad.y : ad.z);
+  }
+  if (!found) return 2;
+  // inside <=> p on the inner side of the hit face's plane (the COM is on the inner side of every face)
+  const float3 n = cross3(f3(B.x - A.x, B.y - A.y, B.z - A.z), f3(C.x - A.x, C.y - A.y, C.z - A.z));
+  const float W = (dot3(n, f3(u.x - A.x, u.y - A.y, u.z - A.z)) < 0.0f) ? 1.0f : 0.0f;
+  const float rinv = rsqrtf(r2);
+  const float sinp = rho * rinv;
+  const uint16_t *tab = P.ring_tab + (size_t)f * RING_TAB;
+  const uint8_t *rend = P.ring_end + (size_t)f * (RING_MAX + 1);
+  float corr = 0.0f;
+  int jbeg = 0;
+  bool open = true;  // the last examined ring still touched the cone
+  for (int ring = 0; ring <= RING_MAX && open; ring++) {  // uniform within the group: all its lanes hold the same unit
+    const int jend = __ldg(rend + ring);
+    unsigned touched = 0;
+    for (int base = jbeg; base < jend; base += UNIT_LANES) {
+      const int j = base + g;
+      bool hit = false;
+      if (j < jend) {
+      const int gf = __ldg(tab + j);
+      const ushort4 gc = __ldg(P.faces + gf);
+      const float4 q0 = __ldg(Vj + gc.x), q1 = __ldg(Vj + gc.y), q2 = __ldg(Vj + gc.z);
+      const float3 a = f3((q0.x + sh.x) - p.x, (q0.y + sh.y) - p.y, (q0.z + sh.z) - p.z);  // reference: V + shift - p
+      const float3 b = f3((q1.x + sh.x) - p.x, (q1.y + sh.y) - p.y, (q1.z + sh.z) - p.z);
+      const float3 c = f3((q2.x + sh.x) - p.x, (q2.y + sh.y) - p.y, (q2.z + sh.z) - p.z);
+      // Is the face, seen from C, within the cone's half-angle phi of the ray?  Exact test on the sphere of
+      // directions: the ray pierces the spherical triangle, or passes within phi of a corner, or within phi of the
+      // interior of an edge arc (Lagrange identity for (ga x u).(ga x gb) keeps it to dot products).
+      const float3 ga = f3(a.x + u.x, a.y + u.y, a.z + u.z), gb = f3(b.x + u.x, b.y + u.y, b.z + u.z), gc2 = f3(c.x + u.x, c.y + u.y, c.z + u.z);
+      const float ua = dot3(u, ga), ub = dot3(u, gb), uc = dot3(u, gc2);
+      const float aa = dot3(ga, ga), bb = dot3(gb, gb), cc = dot3(gc2, gc2);
+      const float ab = dot3(ga, gb), bc = dot3(gb, gc2), ca = dot3(gc2, ga);
+      const float3 n0 = cross3(ga, gb), n1 = cross3(gb, gc2), n2 = cross3(gc2, ga);
+      const float e0 = dot3(u, n0), e1 = dot3(u, n1), e2 = dot3(u, n2);
+      const float s2 = sinp * sinp * r2 * 1.002f, c2 = (1.0f - sinp * sinp) * r2 * 0.998f;
+      hit = (e0 >= 0.0f && e1 >= 0.0f && e2 >= 0.0f);
+      hit = hit || (ua > 0.0f && ua * ua >= c2 * aa) || (ub > 0.0f && ub * ub >= c2 * bb) || (uc > 0.0f && uc * uc >= c2 * cc);
+      hit = hit || (e0 < 0.0f && e0 * e0 <= s2 * dot3(n0, n0) && aa * ub - ab * ua >= 0.0f && ua * bb - ub * ab >= 0.0f);
+      hit = hit || (e1 < 0.0f && e1 * e1 <= s2 * dot3(n1, n1) && bb * uc - bc * ub >= 0.0f && ub * cc - uc * bc >= 0.0f);
+      hit = hit || (e2 < 0.0f && e2 * e2 <= s2 * dot3(n2, n2) && cc * ua - ca * uc >= 0.0f && uc * aa - ua * ca >= 0.0f);
+      if (hit) {
+        float den, num;
+        solid_angle_terms(a, b, c, den, num);
+        if (den < 1e-8f) corr += omega_skipped_f64(a, b, c);
+      }
+      }
+      touched |= __ballot_sync(gmask, hit);
+    }
+    open = touched != 0;
+    jbeg = jend;
+  }
+  if (open) return 3;  // the outermost tabulated ring still touches the cone
+  w_out = W - group_sum(corr, gmask) / (4.0f * 3.14159274101257f);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------
 // Per-cell bounds of a position array (used once after upload; afterwards the step
 // kernel's epilogue keeps them current).  One CTA of 128 threads per cell.
 // ---------------------------------------------------------------------------------
+// signed volume of the tetrahedron (C, P0, P1, P2) is positive with a margin for every face  <=>  the mesh is
+// star-shaped about C (closed, consistently oriented): the precondition of winding_fast
+__device__ __forceinline__ bool face_sees_centre(float4 P0, float4 P1, float4 P2, float3 C) {
+  const float3 a = sub3(P0, C), b = sub3(P1, C), c = sub3(P2, C);
+  const float3 cr = cross3(b, c);
+  const float sv = dot3(a, cr);
+  return sv > 0.0f && sv * sv > 1e-6f * dot3(a, a) * dot3(cr, cr);
+}
+
 static __global__ void dpm3d_bounds_kernel(const float4 *pos, float4 *bnd, int nc, int nv, const uint16_t *ring_nbr,
-                                           const uint8_t *valence, int ring_stride) {
+                                           const uint8_t *valence, int ring_stride, const ushort4 *faces, int nf) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 *sP = reinterpret_cast<float4 *>(smem_raw);
   __shared__ float sRed[4][8];
@@ -128,26 +296,38 @@ static __global__ void dpm3d_bounds_kernel(const float4 *pos, float4 *bnd, int n
   if (warp == 0 && lane < 3) sCom[lane] = com_chain(sP, nv, lane);
   __syncthreads();
   float3 com = f3(sCom[0], sCom[1], sCom[2]);
-  float r2 = 0.0f, e2 = 0.0f;
+  float r2 = 0.0f, e2 = 0.0f, r2min = INFINITY;
+  int star = 1;
+  for (int f = tid; f < nf; f += blockDim.x) {
+    const ushort4 fc = faces[f];
+    star &= face_sees_centre(sP[fc.x], sP[fc.y], sP[fc.z], com) ? 1 : 0;
+  }
   for (int v = tid; v < nv; v += blockDim.x) {
     float3 q = sub3(sP[v], com);
     r2 = fmaxf(r2, dot3(q, q));
+    r2min = fminf(r2min, dot3(q, q));
     const int val = valence[v];
     for (int i = 0; i < val; i++) { float3 e = sub3(sP[ring_nbr[(size_t)v * ring_stride + i]], sP[v]); e2 = fmaxf(e2, dot3(e, e)); }
   }
   r2 = warp_max(r2);
   e2 = warp_max(e2);
+  r2min = warp_min(r2min);
   if (lane == 0) { sRed[warp][6] = r2; sRed[warp][7] = e2; }
+  star = __syncthreads_and(star);
+  __shared__ float sMin[4];
+  if (lane == 0) sMin[warp] = r2min;
   __syncthreads();
   if (tid == 0) {
+    for (int w = 1; w < (int)blockDim.x / 32; w++) sMin[0] = fminf(sMin[0], sMin[w]);
+    bnd[BND * (size_t)ci + 3] = make_float4(sMin[0], star ? 1.f : 0.f, 0.f, 0.f);
     for (int w = 1; w < (int)blockDim.x / 32; w++) {
       for (int d = 0; d < 3; d++) { sRed[0][d] = fminf(sRed[0][d], sRed[w][d]); sRed[0][3 + d] = fmaxf(sRed[0][3 + d], sRed[w][3 + d]); }
       sRed[0][6] = fmaxf(sRed[0][6], sRed[w][6]);
       sRed[0][7] = fmaxf(sRed[0][7], sRed[w][7]);
     }
-    bnd[3 * (size_t)ci + 0] = make_float4(sRed[0][0], sRed[0][1], sRed[0][2], sRed[0][6]);
-    bnd[3 * (size_t)ci + 1] = make_float4(sRed[0][3], sRed[0][4], sRed[0][5], CONTACT_PAD * sqrtf(sRed[0][7]));
-    bnd[3 * (size_t)ci + 2] = make_float4(com.x, com.y, com.z, 0.f);
+    bnd[BND * (size_t)ci + 0] = make_float4(sRed[0][0], sRed[0][1], sRed[0][2], sRed[0][6]);
+    bnd[BND * (size_t)ci + 1] = make_float4(sRed[0][3], sRed[0][4], sRed[0][5], CONTACT_PAD * sqrtf(sRed[0][7]));
+    bnd[BND * (size_t)ci + 2] = make_float4(com.x, com.y, com.z, 0.f);
   }
 }
 
@@ -161,8 +341,7 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nv = P.nv, nf = P.nf, K = P.K;
   float4 *sP = reinterpret_cast<float4 *>(smem_raw);
-  float4 *sU = sP + nv;
-  float4 *sShift = sU + (size_t)nv * NW;
+  float4 *sShift = sP + nv;
   float4 *sLo = sShift + K;
   float4 *sHi = sLo + K;
   float4 *sSph = sHi + K;
@@ -179,7 +358,7 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
   const int ci = blockIdx.x;
   const float4 cA = P.cellA[ci], cB = P.cellB[ci];
   const float Kv = cA.x, Ka = cA.y, Ks = cA.z, v0 = cA.w, a0 = cB.x, l0 = cB.y;
-  const float4 bi0 = P.bnd_in[3 * (size_t)ci], bi1 = P.bnd_in[3 * (size_t)ci + 1], bi2 = P.bnd_in[3 * (size_t)ci + 2];
+  const float4 bi0 = P.bnd_in[BND * (size_t)ci], bi1 = P.bnd_in[BND * (size_t)ci + 1], bi2 = P.bnd_in[BND * (size_t)ci + 2];
   const float3 com = f3(bi2.x, bi2.y, bi2.z);
   const float4 *gP = P.pos_in + (size_t)ci * nv;
 
@@ -319,7 +498,8 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
     const int ncand = min(P.cand_count[ci], K);
     for (int k = tid; k < ncand; k += THREADS) {
       const int cj = P.cand[(size_t)ci * K + k];
-      const float4 bj0 = P.bnd_in[3 * (size_t)cj], bj1 = P.bnd_in[3 * (size_t)cj + 1], bj2 = P.bnd_in[3 * (size_t)cj + 2];
+      const float4 bj0 = P.bnd_in[BND * (size_t)cj], bj1 = P.bnd_in[BND * (size_t)cj + 1], bj2 = P.bnd_in[BND * (size_t)cj + 2];
+      const float4 bj3 = P.bnd_in[BND * (size_t)cj + 3];
       float3 sh = f3(0.f, 0.f, 0.f);
       if (P.pbc) {  // shift = L * round((COMi - COMJ) / L)   (:277-281)
         sh.x = P.L * roundf((com.x - bj2.x) / P.L);
@@ -328,8 +508,8 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
       }
       // padded, shifted bounding box of cj: outside it the reference's formula gives exactly zero
       const float pad = bj1.w;  // CONTACT_PAD * (upper bound of cj's longest edge)
-      const float4 lo = make_float4((bj0.x + sh.x) - pad, (bj0.y + sh.y) - pad, (bj0.z + sh.z) - pad, 0.f);
-      const float4 hi = make_float4((bj1.x + sh.x) + pad, (bj1.y + sh.y) + pad, (bj1.z + sh.z) + pad, 0.f);
+      const float4 lo = make_float4((bj0.x + sh.x) - pad, (bj0.y + sh.y) - pad, (bj0.z + sh.z) - pad, pad);
+      const float4 hi = make_float4((bj1.x + sh.x) + pad, (bj1.y + sh.y) + pad, (bj1.z + sh.z) + pad, bj3.y);  // .w: star-shaped
       const bool ov = !(lo.x > bi1.x || hi.x < bi0.x || lo.y > bi1.y || hi.y < bi0.y || lo.z > bi1.z || hi.z < bi0.z);
       sCand[k] = ov ? cj : -1;
       sShift[k] = make_float4(sh.x, sh.y, sh.z, 0.f);
@@ -342,41 +522,29 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
 
     int U = 0, par = 0;
     unsigned long long evals = 0;
+    int nlit = 0;
     // processes the U queued units, then folds their forces into the owning threads
     auto flush = [&]() {
       __syncthreads();
-      for (int u = warp; u < U; u += NW) {
+      // UNIT_LANES lanes per (vertex, neighbour) unit: the group walks together and splits the ring faces
+      const int g = lane & (UNIT_LANES - 1);
+      const unsigned gmask = ((1u << UNIT_LANES) - 1u) << (lane & ~(UNIT_LANES - 1));
+      for (int u = tid / UNIT_LANES; u < U; u += THREADS / UNIT_LANES) {
         const int code = sUnit[u];
         const int v = code & 0xffff, k = code >> 16;
         const int cj = sCand[k];
         const float4 sh = sShift[k];
         const float4 p = sP[v];
+        const float4 sp = sSph[k];
         const float4 *Vj = P.pos_in + (size_t)cj * nv;
-        float4 *myU = sU + (size_t)warp * nv;
-        for (int i = lane; i < nv; i += 32) {
-          const float4 q = __ldg(Vj + i);
-          // a = V + shift - p ; u = normalize(a)   (:285-291)
-          const float ax = (q.x + sh.x) - p.x, ay = (q.y + sh.y) - p.y, az = (q.z + sh.z) - p.z;
-          // near-coplanar faces make the triple product cancel: refine MUFU.RSQ (2 ulp) with one Newton step so the
-          // unit vectors are as accurate as the reference's a / sqrt(dot(a, a))
-          const float d2 = ax * ax + ay * ay + az * az;
-          float r = rsqrtf(d2);
-          r = r * (1.5f - 0.5f * d2 * r * r);
-          myU[i] = make_float4(ax * r, ay * r, az * r, 0.f);
+        float w;
+        int why = -1;  // -1: neighbour not star-shaped about its COM
+        if (sHi[k].w != 0.0f) why = winding_fast(P, Vj, sh, p, f3(sp.x, sp.y, sp.z), sLo[k].w, w, g, gmask);
+        if (why != 0) {
+          w = winding_literal(Vj, P.faces, nf, sh, p, g, gmask);
+          if (g == 0) { nlit++; atomicAdd(&P.st->fallback_why[why < 0 ? 0 : why], 1ull); }
         }
-        __syncwarp();
-        float om = 0.0f;
-        for (int f = lane; f < nf; f += 32) {
-          const ushort4 fc = __ldg(P.faces + f);
-          const float4 a = myU[fc.x], b = myU[fc.y], c = myU[fc.z];
-          const float den = 1.0f + (a.x * b.x + a.y * b.y + a.z * b.z) + (b.x * c.x + b.y * c.y + b.z * c.z) +
-                            (c.x * a.x + c.y * a.y + c.z * a.z);
-          const float num = a.x * (b.y * c.z - b.z * c.y) + a.y * (b.z * c.x - b.x * c.z) + a.z * (b.x * c.y - b.y * c.x);
-          if (!(den < 1e-8f)) om += 2.0f * atan2f(num, den);  // :293-299
-        }
-        om = warp_sum(om);
-        if (lane == 0) sUnitW[u] = om / (4.0f * 3.14159274101257f);
-        __syncwarp();
+        if (g == 0) sUnitW[u] = w;
       }
       __syncthreads();
 #pragma unroll
@@ -436,6 +604,7 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
     }
     if (U > 0) flush();
     if (tid == 0 && evals) atomicAdd(&P.st->contact_evals, evals);
+    if (nlit) atomicAdd(&P.st->literal_evals, (unsigned long long)nlit);
   }
 
   // ---- phase 4: Euler update, outputs, next-step bounds ------------------------------------------
@@ -474,16 +643,26 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
   e2max = warp_max(e2max);
   __syncthreads();
   const float3 ncom = f3(sScalar[1], sScalar[2], sScalar[3]);
-  float r2 = 0.0f;
+  float r2 = 0.0f, r2min = INFINITY;
 #pragma unroll
   for (int j = 0; j < VPT; j++) {
     const int v = tid + j * THREADS;
-    if (v < nv) { const float3 q = sub3(myP[j], ncom); r2 = fmaxf(r2, dot3(q, q)); }
+    if (v < nv) { const float3 q = sub3(myP[j], ncom); const float qq = dot3(q, q); r2 = fmaxf(r2, qq); r2min = fminf(r2min, qq); }
+  }
+  // is the NEW shape star-shaped about its COM?  (precondition of the neighbours' fast contact evaluation next step)
+  int star = 1;
+  for (int f = tid; f < nf; f += THREADS) {
+    const ushort4 fc = __ldg(P.faces + f);
+    star &= face_sees_centre(sP[fc.x], sP[fc.y], sP[fc.z], ncom) ? 1 : 0;
   }
   r2 = warp_max(r2);
-  if (lane == 0) { sRed[warp][6] = r2; sRed[warp][7] = e2max; }
-  __syncthreads();
+  r2min = warp_min(r2min);
+  if (lane == 0) { sRed[warp][6] = r2; sRed[warp][7] = e2max; sScalar[4 + warp] = r2min; }
+  star = __syncthreads_and(star);
   if (tid == 0) {
+    float rmin = sScalar[4];
+    for (int w = 1; w < NW && w < 8; w++) rmin = fminf(rmin, sScalar[4 + w]);
+    P.bnd_out[BND * (size_t)ci + 3] = make_float4(rmin, star ? 1.f : 0.f, 0.f, 0.f);
     float l[3], h[3], rr = sRed[0][6], eb = sRed[0][7];
     for (int d = 0; d < 3; d++) { l[d] = sRed[0][d]; h[d] = sRed[0][3 + d]; }
     for (int w = 1; w < NW; w++) {
@@ -492,10 +671,10 @@ __global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
       eb = fmaxf(eb, sRed[w][7]);
     }
     const float pad = CONTACT_PAD * sqrtf(eb);
-    P.bnd_out[3 * (size_t)ci + 0] = make_float4(l[0], l[1], l[2], rr);
-    P.bnd_out[3 * (size_t)ci + 1] = make_float4(h[0], h[1], h[2], pad);
+    P.bnd_out[BND * (size_t)ci + 0] = make_float4(l[0], l[1], l[2], rr);
+    P.bnd_out[BND * (size_t)ci + 1] = make_float4(h[0], h[1], h[2], pad);
     if (pad > P.st->range) P.st->rebuild = 1;  // the candidate lists were built for smaller contact pads
-    P.bnd_out[3 * (size_t)ci + 2] = make_float4(ncom.x, ncom.y, ncom.z, sScalar[0]);
+    P.bnd_out[BND * (size_t)ci + 2] = make_float4(ncom.x, ncom.y, ncom.z, sScalar[0]);
     const float4 bl = P.bbox_lo[ci], bh = P.bbox_hi[ci];
     if (l[0] < bl.x || l[1] < bl.y || l[2] < bl.z || h[0] > bh.x || h[1] > bh.y || h[2] > bh.z) P.st->rebuild = 1;
   }

@@ -28,6 +28,8 @@ struct NbrState {
   int nbuilds;
   int pad;
   unsigned long long contact_evals;
+  unsigned long long literal_evals;  // 3D: units that needed the literal all-faces sum (fallback of the fast path)
+  unsigned long long fallback_why[4];  // [0] neighbour not star-shaped, [1] vertex within the pad of the COM, [2] walk limit, [3] ring limit
   // global raw (unwrapped) extent, for the 2D |d|>L partner search
   float glo[3];
   float ghi[3];

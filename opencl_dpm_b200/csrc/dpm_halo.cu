@@ -82,7 +82,7 @@ static Nccl &nccl() {
 // message layout for capacity C cells and nv vertices per cell (all sections 16-byte aligned, C % 4 == 0)
 __host__ __device__ inline size_t msg_off_gid() { return sizeof(int) * HDR_INTS; }
 __host__ __device__ inline size_t msg_off_bnd(int C) { return msg_off_gid() + sizeof(int) * (size_t)C; }
-__host__ __device__ inline size_t msg_off_pos(int C) { return msg_off_bnd(C) + sizeof(float4) * 3 * (size_t)C; }
+__host__ __device__ inline size_t msg_off_pos(int C) { return msg_off_bnd(C) + sizeof(float4) * BND * (size_t)C; }
 __host__ __device__ inline size_t msg_size(int C, int nv) { return msg_off_pos(C) + sizeof(float4) * (size_t)nv * C; }
 
 // ---- 1. per-rank summary -------------------------------------------------------------------------------------
@@ -90,7 +90,7 @@ __global__ void shard_prepare_kernel(const float4 *bnd, int n_own, const NbrStat
   __shared__ float s[8][4];
   float rlo = INFINITY, rhi = -INFINITY, ext = 0.f, pad = 0.f;
   for (int c = threadIdx.x; c < n_own; c += blockDim.x) {
-    const float4 lo = bnd[3 * (size_t)c], hi = bnd[3 * (size_t)c + 1];
+    const float4 lo = bnd[BND * (size_t)c], hi = bnd[BND * (size_t)c + 1];
     rlo = fminf(rlo, lo.x); rhi = fmaxf(rhi, hi.x);
     ext = fmaxf(ext, fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z)));
     pad = fmaxf(pad, hi.w);
@@ -142,7 +142,7 @@ __global__ void shard_select_kernel(const float4 *bnd, int n_own, NbrState *st, 
     const int c = c0 + threadIdx.x;
     bool want[2] = {false, false};
     if (c < n_own) {
-      const float4 lo = bnd[3 * (size_t)c], hi = bnd[3 * (size_t)c + 1];
+      const float4 lo = bnd[BND * (size_t)c], hi = bnd[BND * (size_t)c + 1];
       for (int p = 0; p < npeers; p++) want[p] = reaches(lo.x, hi.x, margin, all[peers[p] * GATHER + 1], all[peers[p] * GATHER + 2], pbc, L);
       // a cell that reaches a slab which is not an adjacent one cannot be served by this ring exchange
       for (int r = 0; r < nranks; r++)
@@ -180,7 +180,7 @@ __global__ void shard_pack_kernel(const float4 *pos, const float4 *bnd, const in
   if (s >= cnt) return;
   const int c = (p == 0 ? list0 : list1)[s];
   if (threadIdx.x == 0) reinterpret_cast<int *>(buf + msg_off_gid())[s] = gid[c];
-  if (threadIdx.x < 3) reinterpret_cast<float4 *>(buf + msg_off_bnd(cap))[3 * s + threadIdx.x] = bnd[3 * (size_t)c + threadIdx.x];
+  if (threadIdx.x < BND) reinterpret_cast<float4 *>(buf + msg_off_bnd(cap))[BND * s + threadIdx.x] = bnd[BND * (size_t)c + threadIdx.x];
   float4 *dst = reinterpret_cast<float4 *>(buf + msg_off_pos(cap)) + (size_t)s * nv;
   const float4 *src = pos + (size_t)c * nv;
   for (int v = threadIdx.x; v < nv; v += blockDim.x) dst[v] = src[v];
@@ -198,7 +198,7 @@ __global__ void shard_unpack_kernel(float4 *pos, float4 *bnd, int *gid, ShardDev
   const unsigned char *buf = p == 0 ? buf0 : buf1;
   const int c = n_own + (p == 0 ? 0 : cnt0) + s;
   if (threadIdx.x == 0) gid[c] = reinterpret_cast<const int *>(buf + msg_off_gid())[s];
-  if (threadIdx.x < 3) bnd[3 * (size_t)c + threadIdx.x] = reinterpret_cast<const float4 *>(buf + msg_off_bnd(cap))[3 * s + threadIdx.x];
+  if (threadIdx.x < BND) bnd[BND * (size_t)c + threadIdx.x] = reinterpret_cast<const float4 *>(buf + msg_off_bnd(cap))[BND * s + threadIdx.x];
   const float4 *src = reinterpret_cast<const float4 *>(buf + msg_off_pos(cap)) + (size_t)s * nv;
   float4 *dst = pos + (size_t)c * nv;
   for (int v = threadIdx.x; v < nv; v += blockDim.x) dst[v] = src[v];
@@ -292,7 +292,7 @@ int dpm3d_shard_init(dpm3d_t *h, int rank, int nranks, const uint8_t id[128], in
   void **grow[] = {(void **)&h->pos[0], (void **)&h->pos[1], (void **)&h->bnd[0], (void **)&h->bnd[1], (void **)&h->bbox_lo,
                    (void **)&h->bbox_hi, (void **)&h->bin_id, (void **)&h->order, (void **)&h->bin_count, (void **)&h->bin_start};
   h->cap = 4 * h->nslots + 1024;
-  const size_t sizes[] = {sizeof(float4) * nvert, sizeof(float4) * nvert, sizeof(float4) * 3 * h->nslots, sizeof(float4) * 3 * h->nslots,
+  const size_t sizes[] = {sizeof(float4) * nvert, sizeof(float4) * nvert, sizeof(float4) * BND * h->nslots, sizeof(float4) * BND * h->nslots,
                           sizeof(float4) * h->nslots, sizeof(float4) * h->nslots, sizeof(int) * h->nslots, sizeof(int) * h->nslots,
                           sizeof(int) * (h->cap + 1), sizeof(int) * (h->cap + 1)};
   for (int i = 0; i < 10; i++) {

@@ -246,13 +246,12 @@ static void FN(forces3d_range)(int nc, int nv, int nf, const uint32_t *faces, co
           const REAL *comj = coms + 3 * cj;
           if (cand) {
             /* exact per-vertex cull.  The reference drops every face with denom < 1e-8, i.e. every face that
-             * subtends more than pi steradians (:293-295), so its "winding number" is the true one (0 outside)
-             * only when no face is that close.  A face lies within (2/3) e of its centroid (e = its longest edge);
-             * a ball of that radius subtends < pi beyond (2/sqrt 3)(2/3) e = 0.7698 e from its centre, and all
-             * centroids are inside the cell's AABB.  Hence: p farther than 0.775 * emax(cj) from the (shifted)
-             * AABB of cj => every denom > 0 and wn == 0 in exact arithmetic. */
+             * subtends at least pi steradians (:293-295), so w_ref = W - (1/4pi) sum_{skipped} Omega.  A planar
+             * triangle subtends >= pi only if the vertex projects inside it and is within R/sqrt(3) <= e/3 of its
+             * plane (R <= e/sqrt(3): enclosing circle, e: longest edge).  Hence: p farther than 0.34 * emax(cj) from
+             * the (shifted) AABB of cj => no face skipped and W = 0  =>  wn == 0 in exact arithmetic. */
             int out = 0;
-            REAL pad = (REAL)0.775f * emax[cj];
+            REAL pad = (REAL)0.34f * emax[cj];
             for (int d = 0; d < 3; d++) {
               REAL sh = PBC ? L * RROUND((comi[d] - comj[d]) / L) : (REAL)0.0;
               REAL l = (lo[3 * cj + d] + sh) - pad, h = (hi[3 * cj + d] + sh) + pad;

@@ -95,7 +95,7 @@ def test_kat_reference_drops_faces_subtending_more_than_pi():
     b[0, :3] = c + 0.02 * n  # 0.02 outside the face: face subtends > pi -> dropped -> |wn| ~ 0.4
     Fo = O.forces3d(np.concatenate([a, b]), *args, which=8, dtype=np.float64)
     assert 2.0 < np.linalg.norm(Fo[162, :3]) < 6.3
-    b[0, :3] = c + 0.5 * n  # far enough (> 0.775 * longest edge from every centroid): every face counted, true winding number 0
+    b[0, :3] = c + 0.5 * n  # far enough (> longest edge / 3): every face counted, true winding number 0
     Fo = O.forces3d(np.concatenate([a, b]), *args, which=8, dtype=np.float64)
     assert np.abs(Fo[162]).max() == 0.0
 
@@ -138,7 +138,7 @@ def test_culled_equals_all_pairs_3d(pbc):
     args = (d["verts"], d["faces"], *[d[k] for k in PK3], 25.0, pbc, d["L"])
     Fa, ca = O.forces3d(*args, want_contacts=True)
     lo, hi = O.aabb3d(d["verts"], d["nc"])
-    cl = O.cell_list(3, lo, hi, pbc, d["L"], 0.1, 1.25 * 0.775 * 0.36, 32)
+    cl = O.cell_list(3, lo, hi, pbc, d["L"], 0.1, 1.25 * 0.34 * 0.36, 32)
     assert cl["cand_count"].max() <= 32
     Fc, cc = O.forces3d(*args, cand_count=cl["cand_count"], cand=cl["cand"], want_contacts=True)
     assert ca[:, 0].sum() > 50

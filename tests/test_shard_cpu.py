@@ -32,7 +32,7 @@ def _worker(rank, world, port, nx, ny, out):
         for a, b in ((f[0], f[1]), (f[1], f[2]), (f[2], f[0])):
             emax = max(emax, float(np.linalg.norm(V[:, a, :3] - V[:, b, :3], axis=1).max()))
     summary = [None] * world
-    dist.all_gather_object(summary, dict(rlo=float(lo[:, 0].min()), rhi=float(hi[:, 0].max()), ext=float((hi - lo).max()), pad=0.775 * emax))
+    dist.all_gather_object(summary, dict(rlo=float(lo[:, 0].min()), rhi=float(hi[:, 0].max()), ext=float((hi - lo).max()), pad=0.34 * emax))
     margin = shard.halo_margin(max(s["ext"] for s in summary), max(s["pad"] for s in summary))
     peers = sorted({(rank - 1) % world, (rank + 1) % world} - {rank})
     send = {p: shard.select_halo(lo, hi, (summary[p]["rlo"], summary[p]["rhi"]), margin, 1, float(d["L"])) for p in peers}
