@@ -147,7 +147,8 @@ int dpm3d_get_neighbor_artifacts(dpm3d_t *h, dpm_grid_t *grid, int32_t *bin_id, 
 /* Forces a rebuild of the lists from the current positions (asynchronous). */
 int dpm3d_rebuild_neighbors(dpm3d_t *h, int pbc, float L);
 /* Per-cell scalars of the current state: bounds12 = ncells*12 floats
- * {lo.xyz, r2max, hi.xyz, 0, com.xyz, volume}; volume is that of the last step's start. Syncs. */
+ * {lo.xyz, r2max, hi.xyz, contact pad, com.xyz, volume}; COM and volume are evaluated in the reference's serial
+ * summation order with individually rounded operations (bit-comparable with the CPU oracle). Syncs. */
 int dpm3d_get_cell_bounds(dpm3d_t *h, float *bounds12);
 int dpm3d_get_stats(dpm3d_t *h, dpm_stats_t *out);
 int dpm3d_reset_stats(dpm3d_t *h);

@@ -128,46 +128,29 @@ void build_dir_table(int nv, int nf, const uint32_t *faces, const float *verts4_
     }
 }
 
-template <int T, int V>
-cudaError_t launch_step_t(const Step3DParams &p, size_t smem, cudaStream_t s) {
-  dpm3d_step_kernel<T, V><<<p.nc, T, smem, s>>>(p);
-  return cudaGetLastError();
-}
-template <int T, int V>
-cudaError_t set_smem_t(size_t smem) {
-  return cudaFuncSetAttribute(dpm3d_step_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-}
-
 int pick_config(dpm3d_ctx *h) {
-  const int nv = h->nv;
-  if (nv <= 192) { h->threads = 192; h->vpt = 1; }
-  else if (nv <= 1024) { h->threads = 256; h->vpt = (nv + 255) / 256; }
-  else return fail(DPM_ERR_INVALID_ARGUMENT, "meshes with more than 1024 vertices per cell are not supported yet");
+  if (h->nv > 1024) return fail(DPM_ERR_INVALID_ARGUMENT, "meshes with more than 1024 vertices per cell are not supported yet");
+  h->threads = STEP_THREADS; h->vpt = (h->nv + STEP_THREADS - 1) / STEP_THREADS;
   return DPM_OK;
 }
 
-size_t smem_for(dpm3d_ctx *h) {
-  return h->threads == 192 ? step3d_smem_bytes<192>(h->nv, h->nf, h->K) : step3d_smem_bytes<256>(h->nv, h->nf, h->K);
-}
+size_t smem_for(dpm3d_ctx *h) { return step3d_smem_bytes(h->nv, h->nf); }
 
 cudaError_t set_smem(dpm3d_ctx *h) {
-  if (h->threads == 192) return set_smem_t<192, 1>(h->smem);
-  switch (h->vpt) {
-    case 1: return set_smem_t<256, 1>(h->smem);
-    case 2: return set_smem_t<256, 2>(h->smem);
-    case 3: return set_smem_t<256, 3>(h->smem);
-    default: return set_smem_t<256, 4>(h->smem);
-  }
+  cudaError_t e = cudaFuncSetAttribute(dpm3d_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dpm3d_bounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
 }
 
 cudaError_t launch_step(dpm3d_ctx *h, const Step3DParams &p) {
-  if (h->threads == 192) return launch_step_t<192, 1>(p, h->smem, h->stream);
-  switch (h->vpt) {
-    case 1: return launch_step_t<256, 1>(p, h->smem, h->stream);
-    case 2: return launch_step_t<256, 2>(p, h->smem, h->stream);
-    case 3: return launch_step_t<256, 3>(p, h->smem, h->stream);
-    default: return launch_step_t<256, 4>(p, h->smem, h->stream);
-  }
+  dpm3d_step_kernel<<<p.nc, STEP_THREADS, h->smem, h->stream>>>(p);
+  return cudaGetLastError();
+}
+
+CellTopo cell_topo(dpm3d_ctx *h) {
+  CellTopo T;
+  T.faces = h->faces; T.ring_nbr = h->ring_nbr; T.valence = h->valence; T.ring_stride = h->ring_stride; T.nv = h->nv; T.nf = h->nf;
+  return T;
 }
 
 NbrBuffers nbr_buffers(dpm3d_ctx *h, int pbc, float L) {
@@ -186,6 +169,18 @@ NbrBuffers nbr_buffers(dpm3d_ctx *h, int pbc, float L) {
   nb.pbc = pbc; nb.L = L; nb.skin_rel = h->skin_rel; nb.range = 0.0f; nb.far2d = 0;
   nb.range_from_bounds = 1; nb.range_scale = RANGE_HEADROOM;
   return nb;
+}
+
+int alloc_units(dpm3d_ctx *h, int per_cell) {
+  if (h->unit_rec && per_cell <= h->unit_per_cell) return DPM_OK;
+  if (h->unit_rec) cudaFree(h->unit_rec);
+  if (h->unit_w) cudaFree(h->unit_w);
+  h->unit_rec = nullptr; h->unit_w = nullptr;
+  h->unit_per_cell = per_cell;
+  h->unit_cap = (int)std::min<long long>((long long)h->nc * per_cell, 1ll << 30);
+  DPM_CUDA_TRY(cudaMalloc(&h->unit_rec, sizeof(int2) * (size_t)h->unit_cap));
+  DPM_CUDA_TRY(cudaMalloc(&h->unit_w, sizeof(float) * (size_t)h->unit_cap));
+  return DPM_OK;
 }
 
 int alloc_cand(dpm3d_ctx *h) {
@@ -279,6 +274,16 @@ int dpm3d_create(dpm3d_t **out, int device, int ncells, int nv, int nf, const ui
   TRYB(cudaMalloc(&h->chunk_sum, sizeof(int) * h->coop_grid));
   rc = alloc_cand(h);
   if (rc) return bail(rc);
+  TRYB(cudaMalloc(&h->unit_base, sizeof(int) * ncells));
+  TRYB(cudaMalloc(&h->unit_cnt, sizeof(int) * ncells));
+  TRYB(cudaMemset(h->unit_cnt, 0, sizeof(int) * ncells));
+  rc = alloc_units(h, std::min(4096, std::max(256, 4 * nv)));
+  if (rc) return bail(rc);
+  {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    h->contact_grid = sms * 8;
+  }
   h->smem = smem_for(h);
   TRYB(set_smem(h));
 #undef TRYB
@@ -293,7 +298,7 @@ int dpm3d_destroy(dpm3d_t *h) {
   shard_free(h);
   void *ptrs[] = {h->pos[0], h->pos[1], h->force, h->bnd[0], h->bnd[1], h->cellA, h->cellB, h->faces, h->ring_nbr, h->ring_face,
                   h->valence, h->face_adj, h->ring_tab, h->ring_end, h->dir_table, h->st, h->bbox_lo, h->bbox_hi, h->bin_id, h->order, h->bin_count, h->bin_start, h->cand_count,
-                  h->cand, h->partial, h->chunk_sum};
+                  h->cand, h->partial, h->chunk_sum, h->unit_rec, h->unit_w, h->unit_base, h->unit_cnt};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (h->h_cell) cudaFreeHost(h->h_cell);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -359,8 +364,7 @@ static int upload_common(dpm3d_t *h, const float *verts4, bool on_device, const 
     DPM_CUDA_TRY(cudaMemcpyAsync(h->dir_table, tab.data(), sizeof(uint16_t) * tab.size(), cudaMemcpyHostToDevice, h->stream));
     DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
-  dpm3d_bounds_kernel<<<h->nc, 128, sizeof(float4) * h->nv, h->stream>>>(h->pos[0], h->bnd[0], h->nc, h->nv, h->ring_nbr,
-                                                                          h->valence, h->ring_stride, h->faces, h->nf);
+  dpm3d_bounds_kernel<<<h->nc, STEP_THREADS, h->smem, h->stream>>>(h->pos[0], h->bnd[0], h->nc, cell_topo(h));
   DPM_CUDA_TRY(cudaGetLastError());
   h->stats.launches += 1;
   h->stats.steps = 0; h->stats.rebuilds = 0; h->stats.contact_evals = 0;  // per-upload counters (launches stay cumulative)
@@ -406,6 +410,8 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
   p.face_adj = h->face_adj; p.ring_tab = h->ring_tab; p.ring_end = h->ring_end; p.dir_table = h->dir_table;
   p.cand_count = h->cand_count; p.cand = h->cand; p.K = h->K;
   p.bbox_lo = h->bbox_lo; p.bbox_hi = h->bbox_hi; p.st = h->st;
+  p.unit_rec = h->unit_rec; p.unit_w = h->unit_w; p.unit_base = h->unit_base; p.unit_cnt = h->unit_cnt; p.unit_cap = h->unit_cap;
+  const bool repel = (h->mask & DPM3D_REPEL) && Kre != 0.0f;
   p.nc = h->nc; p.nv = h->nv; p.nf = h->nf; p.dt = dt; p.Kc = Kre; p.pbc = pbc; p.L = L; p.mask = h->mask;
   p.stale_from = h->stale_from;
   if (pbc != h->last_pbc || L != h->last_L) {  // the lists depend on the box: rebuild when the caller changed it
@@ -422,11 +428,16 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
     p.pos_in = h->pos[h->cur]; p.pos_out = h->pos[h->cur ^ 1];
     p.bnd_in = h->bnd[h->cur]; p.bnd_out = h->bnd[h->cur ^ 1];
     p.force_out = (s == nsteps - 1) ? h->force : nullptr;  // forces are only read back after the last step (:425-434)
+    if (repel) {
+      dpm3d_units_kernel<<<h->nc, UNITS_THREADS, 0, h->stream>>>(p);
+      dpm3d_contact_kernel<<<h->contact_grid, CONTACT_THREADS, 0, h->stream>>>(p);
+      DPM_CUDA_TRY(cudaGetLastError());
+    }
     DPM_CUDA_TRY(launch_step(h, p));
     h->cur ^= 1;
   }
   h->stats.steps += (uint64_t)nsteps;
-  h->stats.launches += 2ull * (uint64_t)nsteps;
+  h->stats.launches += (repel ? 4ull : 2ull) * (uint64_t)nsteps;
   return DPM_OK;
 }
 
@@ -440,6 +451,7 @@ static int check_device_flags(dpm3d_t *h) {
   h->stats.reserved[1] = st.fallback_why[0] | (st.fallback_why[1] << 32);  // diagnostics: not-star | near-COM
   h->stats.reserved[2] = st.fallback_why[2] | (st.fallback_why[3] << 32);  //              walk limit | ring limit
   if (st.overflow) return fail(DPM_ERR_RUNTIME, "neighbour candidate list overflow: raise max_candidates (dpm3d_set_neighbor_params)");
+  if (st.unit_overflow) return fail(DPM_ERR_RUNTIME, "contact unit queue overflow");
   if (h->nranks > 1) return shard_check(h);
   return DPM_OK;
 }
@@ -481,10 +493,19 @@ int dpm3d_euler_update(dpm3d_t *h, float *verts4, float *forces4, const float *K
     if (rc) return rc;
     DPM_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     rc = check_device_flags(h);
-    if (rc == DPM_ERR_RUNTIME && h->K < 128 && attempt < 3) {  // candidate overflow: grow K and redo from the host state
-      int rc2 = dpm3d_set_neighbor_params(h, h->skin_rel, std::min(128, h->K * 2));
-      if (rc2) return rc2;
-      continue;
+    if (rc == DPM_ERR_RUNTIME && attempt < 3) {  // a capacity was exceeded: grow it and redo from the host state
+      char msg[256];
+      dpm_last_error(msg, sizeof msg);
+      if (strstr(msg, "contact unit")) {
+        int rc2 = alloc_units(h, h->unit_per_cell * 4);
+        if (rc2) return rc2;
+        continue;
+      }
+      if (strstr(msg, "candidate list") && h->K < 128) {
+        int rc2 = dpm3d_set_neighbor_params(h, h->skin_rel, std::min(128, h->K * 2));
+        if (rc2) return rc2;
+        continue;
+      }
     }
     if (rc) return rc;
     break;

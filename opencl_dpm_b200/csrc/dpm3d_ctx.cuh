@@ -27,6 +27,11 @@ struct dpm3d_ctx {
   uint8_t *ring_end = nullptr;
   uint16_t *dir_table = nullptr;   // rebuilt at every upload from cell 0
   std::vector<uint32_t> h_faces;
+  int2 *unit_rec = nullptr;  // contact-unit queue (dpm3d_units_kernel -> dpm3d_contact_kernel -> dpm3d_step_kernel)
+  float *unit_w = nullptr;
+  int *unit_base = nullptr, *unit_cnt = nullptr;
+  int unit_cap = 0, unit_per_cell = 0;
+  int contact_grid = 0;
   // neighbour search
   NbrState *st = nullptr;
   float4 *bbox_lo = nullptr, *bbox_hi = nullptr;

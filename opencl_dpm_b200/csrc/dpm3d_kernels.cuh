@@ -47,6 +47,13 @@ struct Step3DParams {
   const float4 *__restrict__ bbox_lo;
   const float4 *__restrict__ bbox_hi;
   NbrState *st;
+  // contact units: (global vertex id, neighbour cell) pairs that survive the culls, built by dpm3d_units_kernel in a
+  // per-cell contiguous range [unit_base[ci], +unit_cnt[ci]) of one global list, evaluated by dpm3d_contact_kernel
+  int2 *__restrict__ unit_rec;
+  float *__restrict__ unit_w;
+  int *__restrict__ unit_base;
+  int *__restrict__ unit_cnt;
+  int unit_cap;
   int nc;  // cells stepped by this launch (owned)
   int nv, nf;
   float dt, Kc;
@@ -81,21 +88,9 @@ __device__ __forceinline__ float group_sum(float v, unsigned gmask) {
   return v;
 }
 
-template <int THREADS>
-size_t step3d_smem_bytes(int nv, int nf, int K) {
-  size_t b = 0;
-  b += sizeof(float4) * nv;                      // sP
-  b += sizeof(float) * nf;                       // sTerm
-  b += sizeof(float4) * K * 3;                   // per-candidate shift / lo / hi
-  b += sizeof(float4) * K;                       // per-candidate sphere (com+shift, r2)
-  b += sizeof(int) * K;                          // candidate ids
-  b += sizeof(int) * UNIT_CAP_FACTOR * THREADS;  // unit codes
-  b += sizeof(float) * UNIT_CAP_FACTOR * THREADS;  // unit winding numbers
-  b += ((nf + 15) / 16) * 16;                    // sFlag
-  return b + 64;
+inline size_t step3d_smem_bytes(int nv, int nf) {
+  return sizeof(float4) * 2 * (size_t)nv + sizeof(float) * nf + ((nf + 15) / 16) * 16 + 64;  // sP, sF, sTerm, sFlag
 }
-
-
 
 __device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
 __device__ __forceinline__ float3 sub3(float4 a, float4 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
@@ -264,9 +259,144 @@ __device__ __forceinline__ int winding_fast(const Step3DParams &P, const float4 
 }
 
 // ---------------------------------------------------------------------------------
-// Per-cell bounds of a position array (used once after upload; afterwards the step
-// kernel's epilogue keeps them current).  One CTA of 128 threads per cell.
+// K1a: contact units.  One CTA per cell: every vertex is tested against the padded bounding box and sphere of each
+// candidate neighbour (cell list) whose box overlaps the cell's own; survivors are written, ordered by (thread,
+// vertex, ascending neighbour), into a contiguous range of the global unit list reserved with one atomicAdd.
 // ---------------------------------------------------------------------------------
+constexpr int UNITS_THREADS = 256;
+constexpr int UNITS_VPT = 4;  // nv <= 1024
+constexpr int UNITS_KMAX = 128;
+
+static __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams P) {
+  __shared__ float4 sLo[UNITS_KMAX], sHi[UNITS_KMAX], sSph[UNITS_KMAX];
+  __shared__ int sCand[UNITS_KMAX];
+  __shared__ int sWarp[UNITS_THREADS / 32];
+  __shared__ int sBase;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ci = blockIdx.x, nv = P.nv, K = P.K;
+  const float4 bi0 = P.bnd_in[BND * (size_t)ci], bi1 = P.bnd_in[BND * (size_t)ci + 1], bi2 = P.bnd_in[BND * (size_t)ci + 2];
+  const int ncand = min(P.cand_count[ci], K);
+  int nact = 0;
+  for (int k = tid; k < ncand; k += UNITS_THREADS) {
+    const int cj = P.cand[(size_t)ci * K + k];
+    const float4 bj0 = P.bnd_in[BND * (size_t)cj], bj1 = P.bnd_in[BND * (size_t)cj + 1], bj2 = P.bnd_in[BND * (size_t)cj + 2];
+    float3 sh = f3(0.f, 0.f, 0.f);
+    if (P.pbc) {  // shift = L * round((COMi - COMJ) / L)   (:277-281)
+      sh.x = P.L * roundf((bi2.x - bj2.x) / P.L);
+      sh.y = P.L * roundf((bi2.y - bj2.y) / P.L);
+      sh.z = P.L * roundf((bi2.z - bj2.z) / P.L);
+    }
+    // padded, shifted bounding box / sphere of cj: outside them the reference's formula gives exactly zero
+    const float pad = bj1.w;  // CONTACT_PAD * (longest edge of cj)
+    const float4 lo = make_float4((bj0.x + sh.x) - pad, (bj0.y + sh.y) - pad, (bj0.z + sh.z) - pad, 0.f);
+    const float4 hi = make_float4((bj1.x + sh.x) + pad, (bj1.y + sh.y) + pad, (bj1.z + sh.z) + pad, 0.f);
+    const bool ov = !(lo.x > bi1.x || hi.x < bi0.x || lo.y > bi1.y || hi.y < bi0.y || lo.z > bi1.z || hi.z < bi0.z);
+    sCand[k] = ov ? cj : -1;
+    sLo[k] = lo;
+    sHi[k] = hi;
+    const float rs = sqrtf(bj0.w) + pad;
+    sSph[k] = make_float4(bj2.x + sh.x, bj2.y + sh.y, bj2.z + sh.z, rs * rs * 1.0001f + 1e-30f);
+    nact += ov ? 1 : 0;
+  }
+  if (__syncthreads_or(nact) == 0) {  // no neighbour's box reaches this cell
+    if (tid == 0) { P.unit_base[ci] = 0; P.unit_cnt[ci] = 0; }
+    return;
+  }
+  float4 myp[UNITS_VPT];
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < UNITS_VPT; j++) {
+    const int v = tid + j * UNITS_THREADS;
+    if (v < nv) {
+      const float4 p = P.pos_in[(size_t)ci * nv + v];
+      myp[j] = p;
+      for (int k = 0; k < ncand; k++) {
+        if (sCand[k] < 0) continue;
+        const float4 lo = sLo[k], hi = sHi[k], sp = sSph[k];
+        const float dx = p.x - sp.x, dy = p.y - sp.y, dz = p.z - sp.z;
+        cnt += (!(p.x < lo.x || p.x > hi.x || p.y < lo.y || p.y > hi.y || p.z < lo.z || p.z > hi.z) &&
+                (dx * dx + dy * dy + dz * dz) <= sp.w) ? 1 : 0;
+      }
+    }
+  }
+  // exclusive scan of the per-thread counts
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+  if (lane == 31) sWarp[warp] = incl;
+  __syncthreads();
+  int woff = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < UNITS_THREADS / 32; w++) { const int c = sWarp[w]; if (w < warp) woff += c; total += c; }
+  if (tid == 0) {
+    int base = 0;
+    if (total > 0) {
+      base = atomicAdd(&P.st->unit_total, total);
+      if (base + total > P.unit_cap) { P.st->unit_overflow = 1; base = -1; }
+      else atomicAdd(&P.st->contact_evals, (unsigned long long)total);
+    }
+    sBase = base;
+    P.unit_base[ci] = base < 0 ? 0 : base;
+    P.unit_cnt[ci] = base < 0 ? 0 : total;
+  }
+  __syncthreads();
+  if (total == 0 || sBase < 0) return;
+  int2 *out = P.unit_rec + sBase + woff + incl - cnt;
+#pragma unroll
+  for (int j = 0; j < UNITS_VPT; j++) {
+    const int v = tid + j * UNITS_THREADS;
+    if (v < nv) {
+      const float4 p = myp[j];
+      for (int k = 0; k < ncand; k++) {
+        const int cj = sCand[k];
+        if (cj < 0) continue;
+        const float4 lo = sLo[k], hi = sHi[k], sp = sSph[k];
+        const float dx = p.x - sp.x, dy = p.y - sp.y, dz = p.z - sp.z;
+        if (!(p.x < lo.x || p.x > hi.x || p.y < lo.y || p.y > hi.y || p.z < lo.z || p.z > hi.z) &&
+            (dx * dx + dy * dy + dz * dz) <= sp.w)
+          *out++ = make_int2(ci * nv + v, cj);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// K1b: evaluates every contact unit of the global list, UNIT_LANES lanes per unit, grid-stride (load balanced over
+// the whole GPU instead of per cell).  Writes the reference's "winding number" of the unit.
+// ---------------------------------------------------------------------------------
+constexpr int CONTACT_THREADS = 256;
+
+static __global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(Step3DParams P) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane & (UNIT_LANES - 1);
+  const unsigned gmask = ((1u << UNIT_LANES) - 1u) << (lane & ~(UNIT_LANES - 1));
+  const int ngroups = gridDim.x * (CONTACT_THREADS / UNIT_LANES);
+  const int total = min(P.st->unit_total, P.unit_cap);
+  const int nv = P.nv;
+  for (int u = blockIdx.x * (CONTACT_THREADS / UNIT_LANES) + threadIdx.x / UNIT_LANES; u < total; u += ngroups) {
+    const int2 rec = P.unit_rec[u];
+    const int ci = rec.x / nv, cj = rec.y;
+    const float4 p = P.pos_in[rec.x];
+    const float4 bi2 = P.bnd_in[BND * (size_t)ci + 2];
+    const float4 bj1 = P.bnd_in[BND * (size_t)cj + 1], bj2 = P.bnd_in[BND * (size_t)cj + 2], bj3 = P.bnd_in[BND * (size_t)cj + 3];
+    float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (P.pbc) {  // shift = L * round((COMi - COMJ) / L)   (:277-281)
+      sh.x = P.L * roundf((bi2.x - bj2.x) / P.L);
+      sh.y = P.L * roundf((bi2.y - bj2.y) / P.L);
+      sh.z = P.L * roundf((bi2.z - bj2.z) / P.L);
+    }
+    const float4 *Vj = P.pos_in + (size_t)cj * nv;
+    float w;
+    int why = -1;  // -1: neighbour not star-shaped about its COM
+    if (bj3.y != 0.0f) why = winding_fast(P, Vj, sh, p, f3(bj2.x + sh.x, bj2.y + sh.y, bj2.z + sh.z), bj1.w, w, g, gmask);
+    if (why != 0) {
+      w = winding_literal(Vj, P.faces, P.nf, sh, p, g, gmask);
+      if (g == 0) { atomicAdd(&P.st->literal_evals, 1ull); atomicAdd(&P.st->fallback_why[why < 0 ? 0 : why], 1ull); }
+    }
+    if (g == 0) P.unit_w[u] = w;
+  }
+}
+
 // signed volume of the tetrahedron (C, P0, P1, P2) is positive with a margin for every face  <=>  the mesh is
 // star-shaped about C (closed, consistently oriented): the precondition of winding_fast
 __device__ __forceinline__ bool face_sees_centre(float4 P0, float4 P1, float4 P2, float3 C) {
@@ -276,409 +406,251 @@ __device__ __forceinline__ bool face_sees_centre(float4 P0, float4 P1, float4 P2
   return sv > 0.0f && sv * sv > 1e-6f * dot3(a, a) * dot3(cr, cr);
 }
 
-static __global__ void dpm3d_bounds_kernel(const float4 *pos, float4 *bnd, int nc, int nv, const uint16_t *ring_nbr,
-                                           const uint8_t *valence, int ring_stride, const ushort4 *faces, int nf) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4 *sP = reinterpret_cast<float4 *>(smem_raw);
-  __shared__ float sRed[4][8];
-  __shared__ float sCom[3];
-  const int ci = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// ---------------------------------------------------------------------------------
+// Per-cell scalars of the positions held in shared memory (sP): exact AABB, serial-order COM, serial-order signed
+// volume (both chains run CONCURRENTLY in two different warps), r^2 max/min about the COM, longest edge (-> contact
+// pad) and the star-shape flag.  Used by the bounds kernel (after an upload) and by the step kernel's epilogue (for
+// the NEW positions).  Block of STEP_THREADS threads; sTerm: nf floats of scratch.
+//   bnd[0] = (lo.xyz, r2max)   bnd[1] = (hi.xyz, pad)   bnd[2] = (com.xyz, volume)   bnd[3] = (r2min, star, vol_prev, 0)
+// ---------------------------------------------------------------------------------
+constexpr int STEP_THREADS = 128;
+constexpr int STEP_WARPS = STEP_THREADS / 32;
+
+struct CellTopo {
+  const ushort4 *__restrict__ faces;
+  const uint16_t *__restrict__ ring_nbr;
+  const uint8_t *__restrict__ valence;
+  int ring_stride, nv, nf;
+};
+
+__device__ __forceinline__ void cell_scalars(const float4 *sP, float *sTerm, const CellTopo &T, float vol_prev, float4 *bnd_cell,
+                                             const float4 *bbox_lo, const float4 *bbox_hi, NbrState *st) {
+  __shared__ float sRed[STEP_WARPS][10];
+  __shared__ float sSc[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nv = T.nv, nf = T.nf;
+  // signed-volume terms dot(cross(P0,P1),P2)/6.0f, reference operation order, unfused (shaders/Cell3D_Kernel.cl:58-61)
+  for (int f = tid; f < nf; f += STEP_THREADS) {
+    const ushort4 fc = __ldg(T.faces + f);
+    const float4 P0 = sP[fc.x], P1 = sP[fc.y], P2 = sP[fc.z];
+    const float cx = __fsub_rn(__fmul_rn(P0.y, P1.z), __fmul_rn(P0.z, P1.y));
+    const float cy = __fsub_rn(__fmul_rn(P0.z, P1.x), __fmul_rn(P0.x, P1.z));
+    const float cz = __fsub_rn(__fmul_rn(P0.x, P1.y), __fmul_rn(P0.y, P1.x));
+    sTerm[f] = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, P2.x), __fmul_rn(cy, P2.y)), __fmul_rn(cz, P2.z)), 6.0f);
+  }
+  __syncthreads();
+  if (warp == STEP_WARPS - 1) {  // serial volume chain (:46-64), every lane the same chain (broadcast LDS)
+    float vol = 0.0f;
+    int f = 0;
+    for (; f + 8 <= nf; f += 8) {
+      float t[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) t[q] = sTerm[f + q];
+#pragma unroll
+      for (int q = 0; q < 8; q++) vol = __fadd_rn(vol, t[q]);
+    }
+    for (; f < nf; f++) vol = __fadd_rn(vol, sTerm[f]);
+    if (lane == 0) sSc[3] = fabsf(vol);
+  } else if (warp == STEP_WARPS - 2) {  // serial COM chain (:35-44), one lane per component
+    if (lane < 3) sSc[lane] = com_chain(sP, nv, lane);
+  }
+  // meanwhile (warps 0..): AABB and longest edge
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  for (int v = tid; v < nv; v += blockDim.x) {
-    float4 p = pos[(size_t)ci * nv + v];
-    sP[v] = p;
-    lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
-    hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+  float e2 = 0.0f;
+  if (warp < STEP_WARPS - 2) {
+    for (int v = tid; v < nv; v += 32 * (STEP_WARPS - 2)) {
+      const float4 p = sP[v];
+      lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+      hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+      const int val = __ldg(T.valence + v);
+      const uint16_t *rn = T.ring_nbr + (size_t)v * T.ring_stride;
+      for (int i = 0; i < val; i++) { const float3 e = sub3(sP[__ldg(rn + i)], p); e2 = fmaxf(e2, dot3(e, e)); }
+    }
   }
   for (int d = 0; d < 3; d++) { lo[d] = warp_min(lo[d]); hi[d] = warp_max(hi[d]); }
-  if (lane == 0) for (int d = 0; d < 3; d++) { sRed[warp][d] = lo[d]; sRed[warp][3 + d] = hi[d]; }
+  e2 = warp_max(e2);
+  if (lane == 0) { for (int d = 0; d < 3; d++) { sRed[warp][d] = lo[d]; sRed[warp][3 + d] = hi[d]; } sRed[warp][6] = e2; }
   __syncthreads();
-  if (warp == 0 && lane < 3) sCom[lane] = com_chain(sP, nv, lane);
-  __syncthreads();
-  float3 com = f3(sCom[0], sCom[1], sCom[2]);
-  float r2 = 0.0f, e2 = 0.0f, r2min = INFINITY;
+  const float3 com = f3(sSc[0], sSc[1], sSc[2]);
+  float r2 = 0.0f, r2min = INFINITY;
+  for (int v = tid; v < nv; v += STEP_THREADS) { const float3 q = sub3(sP[v], com); const float qq = dot3(q, q); r2 = fmaxf(r2, qq); r2min = fminf(r2min, qq); }
   int star = 1;
-  for (int f = tid; f < nf; f += blockDim.x) {
-    const ushort4 fc = faces[f];
+  for (int f = tid; f < nf; f += STEP_THREADS) {
+    const ushort4 fc = __ldg(T.faces + f);
     star &= face_sees_centre(sP[fc.x], sP[fc.y], sP[fc.z], com) ? 1 : 0;
   }
-  for (int v = tid; v < nv; v += blockDim.x) {
-    float3 q = sub3(sP[v], com);
-    r2 = fmaxf(r2, dot3(q, q));
-    r2min = fminf(r2min, dot3(q, q));
-    const int val = valence[v];
-    for (int i = 0; i < val; i++) { float3 e = sub3(sP[ring_nbr[(size_t)v * ring_stride + i]], sP[v]); e2 = fmaxf(e2, dot3(e, e)); }
-  }
   r2 = warp_max(r2);
-  e2 = warp_max(e2);
   r2min = warp_min(r2min);
-  if (lane == 0) { sRed[warp][6] = r2; sRed[warp][7] = e2; }
+  if (lane == 0) { sRed[warp][7] = r2; sRed[warp][8] = r2min; }
   star = __syncthreads_and(star);
-  __shared__ float sMin[4];
-  if (lane == 0) sMin[warp] = r2min;
-  __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < (int)blockDim.x / 32; w++) sMin[0] = fminf(sMin[0], sMin[w]);
-    bnd[BND * (size_t)ci + 3] = make_float4(sMin[0], star ? 1.f : 0.f, 0.f, 0.f);
-    for (int w = 1; w < (int)blockDim.x / 32; w++) {
-      for (int d = 0; d < 3; d++) { sRed[0][d] = fminf(sRed[0][d], sRed[w][d]); sRed[0][3 + d] = fmaxf(sRed[0][3 + d], sRed[w][3 + d]); }
-      sRed[0][6] = fmaxf(sRed[0][6], sRed[w][6]);
-      sRed[0][7] = fmaxf(sRed[0][7], sRed[w][7]);
+    float l[3], h[3], em = 0.f, rr = 0.f, rm = INFINITY;
+    for (int d = 0; d < 3; d++) { l[d] = INFINITY; h[d] = -INFINITY; }
+    for (int w = 0; w < STEP_WARPS; w++) {
+      for (int d = 0; d < 3; d++) { l[d] = fminf(l[d], sRed[w][d]); h[d] = fmaxf(h[d], sRed[w][3 + d]); }
+      em = fmaxf(em, sRed[w][6]); rr = fmaxf(rr, sRed[w][7]); rm = fminf(rm, sRed[w][8]);
     }
-    bnd[BND * (size_t)ci + 0] = make_float4(sRed[0][0], sRed[0][1], sRed[0][2], sRed[0][6]);
-    bnd[BND * (size_t)ci + 1] = make_float4(sRed[0][3], sRed[0][4], sRed[0][5], CONTACT_PAD * sqrtf(sRed[0][7]));
-    bnd[BND * (size_t)ci + 2] = make_float4(com.x, com.y, com.z, 0.f);
+    const float pad = CONTACT_PAD * sqrtf(em);
+    bnd_cell[0] = make_float4(l[0], l[1], l[2], rr);
+    bnd_cell[1] = make_float4(h[0], h[1], h[2], pad);
+    bnd_cell[2] = make_float4(com.x, com.y, com.z, sSc[3]);
+    bnd_cell[3] = make_float4(rm, star ? 1.f : 0.f, vol_prev, 0.f);
+    if (st) {  // neighbour-list validity
+      const float4 bl = *bbox_lo, bh = *bbox_hi;
+      if (l[0] < bl.x || l[1] < bl.y || l[2] < bl.z || h[0] > bh.x || h[1] > bh.y || h[2] > bh.z) st->rebuild = 1;
+      if (pad > st->range) st->rebuild = 1;  // the candidate lists were built for smaller contact pads
+    }
   }
 }
 
-// ---------------------------------------------------------------------------------
-// The fused step kernel.
-// ---------------------------------------------------------------------------------
-template <int THREADS, int VPT>
-__global__ void __launch_bounds__(THREADS) dpm3d_step_kernel(Step3DParams P) {
-  constexpr int NW = THREADS / 32;
-  constexpr int UCAP = UNIT_CAP_FACTOR * THREADS;
+static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_bounds_kernel(const float4 *pos, float4 *bnd, int nc, CellTopo T) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nv = P.nv, nf = P.nf, K = P.K;
   float4 *sP = reinterpret_cast<float4 *>(smem_raw);
-  float4 *sShift = sP + nv;
-  float4 *sLo = sShift + K;
-  float4 *sHi = sLo + K;
-  float4 *sSph = sHi + K;
-  float *sTerm = reinterpret_cast<float *>(sSph + K);
-  float *sUnitW = sTerm + nf;
-  int *sUnit = reinterpret_cast<int *>(sUnitW + UCAP);
-  int *sCand = sUnit + UCAP;
-  unsigned char *sFlag = reinterpret_cast<unsigned char *>(sCand + K);
-  __shared__ float sRed[NW][8];
-  __shared__ float sScalar[12];
-  __shared__ int sCnt[2][NW];
+  float *sTerm = reinterpret_cast<float *>(sP + T.nv);
+  const int ci = blockIdx.x;
+  for (int v = threadIdx.x; v < T.nv; v += STEP_THREADS) sP[v] = pos[(size_t)ci * T.nv + v];
+  __syncthreads();
+  cell_scalars(sP, sTerm, T, 0.0f, bnd + BND * (size_t)ci, nullptr, nullptr, nullptr);
+}
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// ---------------------------------------------------------------------------------
+// K2: the fused shape-force + integrate kernel.  One CTA of 128 threads per cell, vertices strided over the threads,
+// positions and force accumulators in shared memory (small register footprint -> 8+ CTAs per SM, which is what
+// hides the two serial chains of the epilogue).
+// ---------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nv = P.nv, nf = P.nf;
+  float4 *sP = reinterpret_cast<float4 *>(smem_raw);
+  float4 *sF = sP + nv;
+  float *sTerm = reinterpret_cast<float *>(sF + nv);
+  unsigned char *sFlag = reinterpret_cast<unsigned char *>(sTerm + nf);
+  const int tid = threadIdx.x;
   const int ci = blockIdx.x;
   const float4 cA = P.cellA[ci], cB = P.cellB[ci];
   const float Kv = cA.x, Ka = cA.y, Ks = cA.z, v0 = cA.w, a0 = cB.x, l0 = cB.y;
-  const float4 bi0 = P.bnd_in[BND * (size_t)ci], bi1 = P.bnd_in[BND * (size_t)ci + 1], bi2 = P.bnd_in[BND * (size_t)ci + 2];
+  const float4 bi2 = P.bnd_in[BND * (size_t)ci + 2], bi3 = P.bnd_in[BND * (size_t)ci + 3];
   const float3 com = f3(bi2.x, bi2.y, bi2.z);
   const float4 *gP = P.pos_in + (size_t)ci * nv;
 
-  // ---- phase 0: stage the vertex ring --------------------------------------------
-  float4 myP[VPT];
-  float3 F[VPT];
-#pragma unroll
-  for (int j = 0; j < VPT; j++) {
-    int v = tid + j * THREADS;
-    F[j] = f3(0.f, 0.f, 0.f);
-    if (v < nv) { myP[j] = gP[v]; sP[v] = myP[j]; } else myP[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  // ---- stage the vertex ring --------------------------------------------------------------------------
+  for (int v = tid; v < nv; v += STEP_THREADS) sP[v] = gP[v];
   __syncthreads();
 
-  // ---- phase 1: per-face pass: signed-volume terms, down-facing and degenerate flags -------
-  const bool doVol = (P.mask & DPM3D_VOLUME) && (Kv != 0.0f);
-  for (int f = tid; f < nf; f += THREADS) {
+  // ---- per-face flags: facing the substrate (StickToSurface :209-214), degenerate edge (:151) ----------
+  for (int f = tid; f < nf; f += STEP_THREADS) {
     const ushort4 fc = __ldg(P.faces + f);
     const float4 P0 = sP[fc.x], P1 = sP[fc.y], P2 = sP[fc.z];
-    // dot(cross(P0,P1),P2)/6.0f with the reference's operation order, unfused (:58-61)
-    float cx = __fsub_rn(__fmul_rn(P0.y, P1.z), __fmul_rn(P0.z, P1.y));
-    float cy = __fsub_rn(__fmul_rn(P0.z, P1.x), __fmul_rn(P0.x, P1.z));
-    float cz = __fsub_rn(__fmul_rn(P0.x, P1.y), __fmul_rn(P0.y, P1.x));
-    float tp = __fadd_rn(__fadd_rn(__fmul_rn(cx, P2.x), __fmul_rn(cy, P2.y)), __fmul_rn(cz, P2.z));
-    sTerm[f] = __fdiv_rn(tp, 6.0f);
     const float3 A = sub3(P1, P0), B = sub3(P2, P0), C = sub3(P2, P1);
     const float3 n = cross3(A, B);
-    const bool down = n.z * rsqrtf(dot3(n, n)) < -0.1f;  // StickToSurface :209-214
-    const bool deg = dot3(A, A) < 1e-24f || dot3(B, B) < 1e-24f || dot3(C, C) < 1e-24f;  // :151
+    const bool down = n.z * rsqrtf(dot3(n, n)) < -0.1f;
+    const bool deg = dot3(A, A) < 1e-24f || dot3(B, B) < 1e-24f || dot3(C, C) < 1e-24f;
     sFlag[f] = (unsigned char)((down ? 1 : 0) | (deg ? 2 : 0));
   }
   __syncthreads();
 
-  // ---- phase 2a: serial volume chain (last warp, all lanes redundantly: broadcast LDS) ------
-  if (warp == NW - 1) {
-    float vol = 0.0f;
-    if (doVol) {
-      int f = 0;
-      for (; f + 8 <= nf; f += 8) {
-        float t[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) t[q] = sTerm[f + q];
-#pragma unroll
-        for (int q = 0; q < 8; q++) vol = __fadd_rn(vol, t[q]);
-      }
-      for (; f < nf; f++) vol = __fadd_rn(vol, sTerm[f]);
-    }
-    if (lane == 0) sScalar[0] = fabsf(vol);
-  }
-
-  // ---- phase 2b: ring pass (edge springs + volume gradient + flag gather) ---------------------
+  // ---- ring pass: every vertex gathers over its constant ring adjacency ---------------------------------
+  const bool doVol = (P.mask & DPM3D_VOLUME) && (Kv != 0.0f);
+  // volume of the CURRENT positions was left in the bounds by the previous epilogue (serial-order chain)
+  const float coef = doVol ? (-Kv * (bi2.w / v0 - 1.0f)) * (1.0f / 6.0f) : 0.0f;  // :85,:106-108
+  // compat mode: faces >= stale_from see the volume of the previous step's start (0 right after an upload)
+  const float dcoef = (doVol && P.stale_from >= 0) ? (-Kv * (bi3.z / v0 - 1.0f)) * (1.0f / 6.0f) - coef : 0.0f;
+  const bool doArea = (P.mask & DPM3D_AREA) && !(Ka < 1e-8f);
+  const bool doStick = (P.mask & DPM3D_STICK) && !(Ks < 1e-12f);
   const float inv_l0 = 1.0f / l0;
-  int ndown[VPT];
-  float3 G[VPT], Gs[VPT];  // volume gradient: all ring faces / ring faces with index >= stale_from (compat mode)
-  float e2max = 0.0f;
-#pragma unroll
-  for (int j = 0; j < VPT; j++) {
-    const int v = tid + j * THREADS;
-    ndown[j] = 0;
-    G[j] = f3(0.f, 0.f, 0.f);
-    Gs[j] = f3(0.f, 0.f, 0.f);
-    if (v < nv) {
-      const int val = __ldg(P.valence + v);
-      const uint16_t *rn = P.ring_nbr + (size_t)v * P.ring_stride;
-      const uint16_t *rf = P.ring_face + (size_t)v * P.ring_stride;
-      unsigned m = 0;
-      for (int i = 0; i < val; i++) m |= (unsigned)sFlag[__ldg(rf + i)] << (2 * i);
-      ndown[j] = __popc(m & 0x55555555u);
-      const float4 Pv = myP[j];
-      float3 T = f3(0.f, 0.f, 0.f), g = f3(0.f, 0.f, 0.f), Qp = f3(0.f, 0.f, 0.f), Q0 = f3(0.f, 0.f, 0.f);
-      for (int i = 0; i < val; i++) {
-        const float4 Pn = sP[__ldg(rn + i)];
-        const float3 E = sub3(Pn, Pv);
-        const float len2 = dot3(E, E);
-        const float rl = rsqrtf(len2);
-        const float dl = len2 * rl * inv_l0 - 1.0f;  // len/l0 - 1  (:156-160)
-        const int ip = (i == 0) ? val - 1 : i - 1;
-        // edge (v, n_i) belongs to ring faces i-1 and i; each contributes unit(E)*dl unless degenerate
-        const float w = (float)(2 - ((m >> (2 * i + 1)) & 1u) - ((m >> (2 * ip + 1)) & 1u));
-        const float s = rl * dl * w;
-        T.x += E.x * s; T.y += E.y * s; T.z += E.z * s;
-        const float3 Q = sub3(Pn, com);
-        if (i == 0) Q0 = Q;
-        else {
-          const float3 c = cross3(Qp, Q);  // gradient of ring face i-1 = (v, n_{i-1}, n_i)
-          g.x += c.x; g.y += c.y; g.z += c.z;
-          if (P.stale_from >= 0 && (int)__ldg(rf + i - 1) >= P.stale_from) { Gs[j].x += c.x; Gs[j].y += c.y; Gs[j].z += c.z; }
-        }
-        Qp = Q;
-      }
-      {
-        const float3 c = cross3(Qp, Q0);  // ring face val-1 = (v, n_{val-1}, n_0)
+  const float scale = doArea ? Ka * sqrtf(a0) / l0 * 0.3f : 0.0f;  // :162
+  const bool doRep = (P.mask & DPM3D_REPEL) && P.Kc != 0.0f;
+  const int ucnt = doRep ? P.unit_cnt[ci] : 0;
+  const int2 *rec = P.unit_rec + (doRep ? P.unit_base[ci] : 0);
+  const float *uw = P.unit_w + (doRep ? P.unit_base[ci] : 0);
+
+  for (int v = tid; v < nv; v += STEP_THREADS) {
+    const int val = __ldg(P.valence + v);
+    const uint16_t *rn = P.ring_nbr + (size_t)v * P.ring_stride;
+    const uint16_t *rf = P.ring_face + (size_t)v * P.ring_stride;
+    unsigned m = 0;
+    for (int i = 0; i < val; i++) m |= (unsigned)sFlag[__ldg(rf + i)] << (2 * i);
+    const int ndown = __popc(m & 0x55555555u);
+    const float4 Pv = sP[v];
+    float3 T = f3(0.f, 0.f, 0.f), g = f3(0.f, 0.f, 0.f), gs = f3(0.f, 0.f, 0.f), Qp = f3(0.f, 0.f, 0.f), Q0 = f3(0.f, 0.f, 0.f);
+    for (int i = 0; i < val; i++) {
+      const float4 Pn = sP[__ldg(rn + i)];
+      const float3 E = sub3(Pn, Pv);
+      const float len2 = dot3(E, E);
+      const float rl = rsqrtf(len2);
+      const float dl = len2 * rl * inv_l0 - 1.0f;  // len/l0 - 1  (:156-160)
+      const int ip = (i == 0) ? val - 1 : i - 1;
+      // edge (v, n_i) belongs to ring faces i-1 and i; each contributes unit(E)*dl unless degenerate
+      const float w = (float)(2 - ((m >> (2 * i + 1)) & 1u) - ((m >> (2 * ip + 1)) & 1u));
+      const float sc = rl * dl * w;
+      T.x += E.x * sc; T.y += E.y * sc; T.z += E.z * sc;
+      const float3 Q = sub3(Pn, com);
+      if (i == 0) Q0 = Q;
+      else {
+        const float3 c = cross3(Qp, Q);  // gradient of ring face i-1 = (v, n_{i-1}, n_i)
         g.x += c.x; g.y += c.y; g.z += c.z;
-        if (P.stale_from >= 0 && (int)__ldg(rf + val - 1) >= P.stale_from) { Gs[j].x += c.x; Gs[j].y += c.y; Gs[j].z += c.z; }
+        if (P.stale_from >= 0 && (int)__ldg(rf + i - 1) >= P.stale_from) { gs.x += c.x; gs.y += c.y; gs.z += c.z; }
       }
-      G[j] = g;
-      if ((P.mask & DPM3D_AREA) && !(Ka < 1e-8f)) {
-        const float scale = Ka * sqrtf(a0) / l0 * 0.3f;  // :162
-        F[j] = f3(T.x * scale, T.y * scale, T.z * scale);
+      Qp = Q;
+    }
+    {
+      const float3 c = cross3(Qp, Q0);  // ring face val-1 = (v, n_{val-1}, n_0)
+      g.x += c.x; g.y += c.y; g.z += c.z;
+      if (P.stale_from >= 0 && (int)__ldg(rf + val - 1) >= P.stale_from) { gs.x += c.x; gs.y += c.y; gs.z += c.z; }
+    }
+    float3 F = f3(T.x * scale + coef * g.x + dcoef * gs.x, T.y * scale + coef * g.y + dcoef * gs.y, T.z * scale + coef * g.z + dcoef * gs.z);
+    if (doStick && ndown > 0) {
+      const float nd = (float)ndown;  // one application per adjacent down-facing face (:226-246)
+      const float h = fabsf(Pv.z);
+      if (Pv.z < 0.0f) F.z += nd * (Ks * h);
+      if (h < l0 * 2.0f) {
+        const float3 ctv = f3(Pv.x - com.x, Pv.y - com.y, 0.0f - com.z);
+        const float ftmp = Ks * (1.0f - h / l0);
+        const float sc = rsqrtf(dot3(ctv, ctv)) * ftmp * nd;
+        F.x += ctv.x * sc; F.y += ctv.y * sc; F.z += ctv.z * sc;
       }
     }
-  }
-  __syncthreads();  // volume chain done
-
-  // ---- phase 2c: volume force + substrate adhesion --------------------------------------------
-  {
-    const float volume = sScalar[0];
-    const float coef = doVol ? (-Kv * (volume / v0 - 1.0f)) * (1.0f / 6.0f) : 0.0f;  // :85,:106-108
-    // compat mode: faces >= stale_from see the volume of the previous step's start (0 right after an upload)
-    const float dcoef = (doVol && P.stale_from >= 0) ? (-Kv * (bi2.w / v0 - 1.0f)) * (1.0f / 6.0f) - coef : 0.0f;
-    const bool doStick = (P.mask & DPM3D_STICK) && !(Ks < 1e-12f);
-#pragma unroll
-    for (int j = 0; j < VPT; j++) {
-      const int v = tid + j * THREADS;
-      if (v < nv) {
-        F[j].x += coef * G[j].x + dcoef * Gs[j].x;
-        F[j].y += coef * G[j].y + dcoef * Gs[j].y;
-        F[j].z += coef * G[j].z + dcoef * Gs[j].z;
-        if (doStick && ndown[j] > 0) {
-          const float4 Pv = myP[j];
-          const float nd = (float)ndown[j];  // one application per adjacent down-facing face (:226-246)
-          const float h = fabsf(Pv.z);
-          if (Pv.z < 0.0f) F[j].z += nd * (Ks * h);
-          if (h < l0 * 2.0f) {
-            const float3 ctv = f3(Pv.x - com.x, Pv.y - com.y, 0.0f - com.z);
-            const float ftmp = Ks * (1.0f - h / l0);
-            const float s = rsqrtf(dot3(ctv, ctv)) * ftmp * nd;
-            F[j].x += ctv.x * s; F[j].y += ctv.y * s; F[j].z += ctv.z * s;
-          }
-        }
-      }
-    }
-  }
-
-  // ---- phase 3: repulsion (winding number) over surviving (vertex, neighbour) units ----------
-  if ((P.mask & DPM3D_REPEL) && P.Kc != 0.0f) {
-    const int ncand = min(P.cand_count[ci], K);
-    for (int k = tid; k < ncand; k += THREADS) {
-      const int cj = P.cand[(size_t)ci * K + k];
-      const float4 bj0 = P.bnd_in[BND * (size_t)cj], bj1 = P.bnd_in[BND * (size_t)cj + 1], bj2 = P.bnd_in[BND * (size_t)cj + 2];
-      const float4 bj3 = P.bnd_in[BND * (size_t)cj + 3];
-      float3 sh = f3(0.f, 0.f, 0.f);
-      if (P.pbc) {  // shift = L * round((COMi - COMJ) / L)   (:277-281)
-        sh.x = P.L * roundf((com.x - bj2.x) / P.L);
-        sh.y = P.L * roundf((com.y - bj2.y) / P.L);
-        sh.z = P.L * roundf((com.z - bj2.z) / P.L);
-      }
-      // padded, shifted bounding box of cj: outside it the reference's formula gives exactly zero
-      const float pad = bj1.w;  // CONTACT_PAD * (upper bound of cj's longest edge)
-      const float4 lo = make_float4((bj0.x + sh.x) - pad, (bj0.y + sh.y) - pad, (bj0.z + sh.z) - pad, pad);
-      const float4 hi = make_float4((bj1.x + sh.x) + pad, (bj1.y + sh.y) + pad, (bj1.z + sh.z) + pad, bj3.y);  // .w: star-shaped
-      const bool ov = !(lo.x > bi1.x || hi.x < bi0.x || lo.y > bi1.y || hi.y < bi0.y || lo.z > bi1.z || hi.z < bi0.z);
-      sCand[k] = ov ? cj : -1;
-      sShift[k] = make_float4(sh.x, sh.y, sh.z, 0.f);
-      sLo[k] = lo;
-      sHi[k] = hi;
-      const float rs = sqrtf(bj0.w) + pad;
-      sSph[k] = make_float4(bj2.x + sh.x, bj2.y + sh.y, bj2.z + sh.z, rs * rs * 1.0001f + 1e-30f);
-    }
-    __syncthreads();
-
-    int U = 0, par = 0;
-    unsigned long long evals = 0;
-    int nlit = 0;
-    // processes the U queued units, then folds their forces into the owning threads
-    auto flush = [&]() {
-      __syncthreads();
-      // UNIT_LANES lanes per (vertex, neighbour) unit: the group walks together and splits the ring faces
-      const int g = lane & (UNIT_LANES - 1);
-      const unsigned gmask = ((1u << UNIT_LANES) - 1u) << (lane & ~(UNIT_LANES - 1));
-      for (int u = tid / UNIT_LANES; u < U; u += THREADS / UNIT_LANES) {
-        const int code = sUnit[u];
-        const int v = code & 0xffff, k = code >> 16;
-        const int cj = sCand[k];
-        const float4 sh = sShift[k];
-        const float4 p = sP[v];
-        const float4 sp = sSph[k];
-        const float4 *Vj = P.pos_in + (size_t)cj * nv;
-        float w;
-        int why = -1;  // -1: neighbour not star-shaped about its COM
-        if (sHi[k].w != 0.0f) why = winding_fast(P, Vj, sh, p, f3(sp.x, sp.y, sp.z), sLo[k].w, w, g, gmask);
-        if (why != 0) {
-          w = winding_literal(Vj, P.faces, nf, sh, p, g, gmask);
-          if (g == 0) { nlit++; atomicAdd(&P.st->fallback_why[why < 0 ? 0 : why], 1ull); }
-        }
-        if (g == 0) sUnitW[u] = w;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int j = 0; j < VPT; j++) {
-        const int v = tid + j * THREADS;
-        if (v < nv) {
-          float3 dir = f3(0.f, 0.f, 0.f);
-          bool have = false;
-          for (int u = 0; u < U; u++) {
-            if ((sUnit[u] & 0xffff) == v) {
-              const float wn = sUnitW[u];
-              if (!(fabsf(wn) < 1e-6f)) {  // :302-308
-                if (!have) {
-                  const float3 d = f3(com.x - myP[j].x, com.y - myP[j].y, com.z - myP[j].z);
-                  const float r = rsqrtf(dot3(d, d));
-                  dir = f3(d.x * r, d.y * r, d.z * r);
-                  have = true;
-                }
-                const float mg = fabsf(wn) * 0.5f * P.Kc;
-                F[j].x += mg * dir.x; F[j].y += mg * dir.y; F[j].z += mg * dir.z;
-              }
+    // fold this vertex's evaluated contact units (ordered by ascending neighbour id: the reference's cj order)
+    if (ucnt > 0) {
+      const int gv = ci * nv + v;
+      float3 dir = f3(0.f, 0.f, 0.f);
+      bool have = false;
+      for (int u = 0; u < ucnt; u++) {
+        if (__ldg(&rec[u].x) == gv) {
+          const float wn = uw[u];
+          if (!(fabsf(wn) < 1e-6f)) {  // :302-308
+            if (!have) {
+              const float3 d = f3(com.x - Pv.x, com.y - Pv.y, com.z - Pv.z);
+              const float r = rsqrtf(dot3(d, d));
+              dir = f3(d.x * r, d.y * r, d.z * r);
+              have = true;
             }
+            const float mg = fabsf(wn) * 0.5f * P.Kc;
+            F.x += mg * dir.x; F.y += mg * dir.y; F.z += mg * dir.z;
           }
         }
-      }
-      evals += U;
-      U = 0;
-      __syncthreads();
-    };
-
-    for (int k = 0; k < ncand; k++) {
-      if (sCand[k] < 0) continue;  // uniform
-      const float4 lo = sLo[k], hi = sHi[k], sp = sSph[k];
-#pragma unroll
-      for (int j = 0; j < VPT; j++) {
-        if (U + THREADS > UCAP) flush();
-        const int v = tid + j * THREADS;
-        bool flag = false;
-        if (v < nv) {
-          const float4 p = myP[j];
-          flag = !(p.x < lo.x || p.x > hi.x || p.y < lo.y || p.y > hi.y || p.z < lo.z || p.z > hi.z);
-          if (flag) {
-            const float dx = p.x - sp.x, dy = p.y - sp.y, dz = p.z - sp.z;
-            flag = (dx * dx + dy * dy + dz * dz) <= sp.w;
-          }
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, flag);
-        if (lane == 0) sCnt[par][warp] = __popc(bal);
-        __syncthreads();
-        int off = U, tot = 0;
-#pragma unroll
-        for (int w = 0; w < NW; w++) { const int c = sCnt[par][w]; if (w < warp) off += c; tot += c; }
-        if (flag) sUnit[off + __popc(bal & ((1u << lane) - 1u))] = v | (k << 16);
-        U += tot;
-        par ^= 1;
       }
     }
-    if (U > 0) flush();
-    if (tid == 0 && evals) atomicAdd(&P.st->contact_evals, evals);
-    if (nlit) atomicAdd(&P.st->literal_evals, (unsigned long long)nlit);
+    sF[v] = make_float4(F.x, F.y, F.z, 0.f);
   }
-
-  // ---- phase 4: Euler update, outputs, next-step bounds ------------------------------------------
   __syncthreads();  // everyone is done reading start-of-step sP
-  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-  for (int j = 0; j < VPT; j++) {
-    const int v = tid + j * THREADS;
-    if (v < nv) {
-      float4 np = myP[j];
-      np.x += F[j].x * P.dt; np.y += F[j].y * P.dt; np.z += F[j].z * P.dt;  // EulerPosition :380
-      np.w = 0.f;
-      P.pos_out[(size_t)ci * nv + v] = np;
-      if (P.force_out) P.force_out[(size_t)ci * nv + v] = make_float4(F[j].x, F[j].y, F[j].z, 0.f);
-      sP[v] = np;
-      myP[j] = np;
-      lo[0] = fminf(lo[0], np.x); lo[1] = fminf(lo[1], np.y); lo[2] = fminf(lo[2], np.z);
-      hi[0] = fmaxf(hi[0], np.x); hi[1] = fmaxf(hi[1], np.y); hi[2] = fmaxf(hi[2], np.z);
-    }
-  }
-  for (int d = 0; d < 3; d++) { lo[d] = warp_min(lo[d]); hi[d] = warp_max(hi[d]); }
-  if (lane == 0) for (int d = 0; d < 3; d++) { sRed[warp][d] = lo[d]; sRed[warp][3 + d] = hi[d]; }
-  __syncthreads();
-  if (warp == NW - 1 && lane < 3) sScalar[1 + lane] = com_chain(sP, nv, lane);
-  // longest edge of the NEW positions (sets next step's contact pad); overlaps the serial COM chain
-  e2max = 0.0f;
-#pragma unroll
-  for (int j = 0; j < VPT; j++) {
-    const int v = tid + j * THREADS;
-    if (v < nv) {
-      const int val = __ldg(P.valence + v);
-      const uint16_t *rn = P.ring_nbr + (size_t)v * P.ring_stride;
-      for (int i = 0; i < val; i++) { const float3 e = sub3(sP[__ldg(rn + i)], myP[j]); e2max = fmaxf(e2max, dot3(e, e)); }
-    }
-  }
-  e2max = warp_max(e2max);
-  __syncthreads();
-  const float3 ncom = f3(sScalar[1], sScalar[2], sScalar[3]);
-  float r2 = 0.0f, r2min = INFINITY;
-#pragma unroll
-  for (int j = 0; j < VPT; j++) {
-    const int v = tid + j * THREADS;
-    if (v < nv) { const float3 q = sub3(myP[j], ncom); const float qq = dot3(q, q); r2 = fmaxf(r2, qq); r2min = fminf(r2min, qq); }
-  }
-  // is the NEW shape star-shaped about its COM?  (precondition of the neighbours' fast contact evaluation next step)
-  int star = 1;
-  for (int f = tid; f < nf; f += THREADS) {
-    const ushort4 fc = __ldg(P.faces + f);
-    star &= face_sees_centre(sP[fc.x], sP[fc.y], sP[fc.z], ncom) ? 1 : 0;
-  }
-  r2 = warp_max(r2);
-  r2min = warp_min(r2min);
-  if (lane == 0) { sRed[warp][6] = r2; sRed[warp][7] = e2max; sScalar[4 + warp] = r2min; }
-  star = __syncthreads_and(star);
-  if (tid == 0) {
-    float rmin = sScalar[4];
-    for (int w = 1; w < NW && w < 8; w++) rmin = fminf(rmin, sScalar[4 + w]);
-    P.bnd_out[BND * (size_t)ci + 3] = make_float4(rmin, star ? 1.f : 0.f, 0.f, 0.f);
-    float l[3], h[3], rr = sRed[0][6], eb = sRed[0][7];
-    for (int d = 0; d < 3; d++) { l[d] = sRed[0][d]; h[d] = sRed[0][3 + d]; }
-    for (int w = 1; w < NW; w++) {
-      for (int d = 0; d < 3; d++) { l[d] = fminf(l[d], sRed[w][d]); h[d] = fmaxf(h[d], sRed[w][3 + d]); }
-      rr = fmaxf(rr, sRed[w][6]);
-      eb = fmaxf(eb, sRed[w][7]);
-    }
-    const float pad = CONTACT_PAD * sqrtf(eb);
-    P.bnd_out[BND * (size_t)ci + 0] = make_float4(l[0], l[1], l[2], rr);
-    P.bnd_out[BND * (size_t)ci + 1] = make_float4(h[0], h[1], h[2], pad);
-    if (pad > P.st->range) P.st->rebuild = 1;  // the candidate lists were built for smaller contact pads
-    P.bnd_out[BND * (size_t)ci + 2] = make_float4(ncom.x, ncom.y, ncom.z, sScalar[0]);
-    const float4 bl = P.bbox_lo[ci], bh = P.bbox_hi[ci];
-    if (l[0] < bl.x || l[1] < bl.y || l[2] < bl.z || h[0] > bh.x || h[1] > bh.y || h[2] > bh.z) P.st->rebuild = 1;
-  }
-}
 
+  // ---- Euler update (EulerPosition :380), outputs ----------------------------------------------------------
+  for (int v = tid; v < nv; v += STEP_THREADS) {
+    const float4 F = sF[v];
+    float4 np = sP[v];
+    np.x += F.x * P.dt; np.y += F.y * P.dt; np.z += F.z * P.dt;
+    np.w = 0.f;
+    P.pos_out[(size_t)ci * nv + v] = np;
+    if (P.force_out) P.force_out[(size_t)ci * nv + v] = F;
+    sP[v] = np;
+  }
+  __syncthreads();
+
+  // ---- next step's per-cell scalars from the NEW positions --------------------------------------------------
+  CellTopo T;
+  T.faces = P.faces; T.ring_nbr = P.ring_nbr; T.valence = P.valence; T.ring_stride = P.ring_stride; T.nv = nv; T.nf = nf;
+  cell_scalars(sP, sTerm, T, bi2.w, P.bnd_out + BND * (size_t)ci, P.bbox_lo + ci, P.bbox_hi + ci, P.st);
+}
 
 }  // namespace dpm

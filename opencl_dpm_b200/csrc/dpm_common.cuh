@@ -29,7 +29,9 @@ struct NbrState {
   int pad;
   unsigned long long contact_evals;
   unsigned long long literal_evals;  // 3D: units that needed the literal all-faces sum (fallback of the fast path)
-  unsigned long long fallback_why[4];  // [0] neighbour not star-shaped, [1] vertex within the pad of the COM, [2] walk limit, [3] ring limit
+  unsigned long long fallback_why[4];
+  int unit_total;     // 3D: contact units queued this step (reset by the rebuild kernel, which runs first every step)
+  int unit_overflow;  // 3D: the global unit list was too small  // [0] neighbour not star-shaped, [1] vertex within the pad of the COM, [2] walk limit, [3] ring limit
   // global raw (unwrapped) extent, for the 2D |d|>L partner search
   float glo[3];
   float ghi[3];

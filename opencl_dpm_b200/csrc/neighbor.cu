@@ -100,6 +100,7 @@ __device__ __forceinline__ bool axis_far(float li, float hi, float lj, float hj,
 }
 
 __global__ void __launch_bounds__(RB_THREADS) nbr_rebuild_kernel(NbrBuffers nb) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) nb.st->unit_total = 0;  // first kernel of every step: reset the contact-unit queue
   if (nb.st->rebuild == 0) return;  // uniform across the grid: nobody reaches a grid sync
   if (nb.nc_dev) nb.nc = *nb.nc_dev;
   cg::grid_group grid = cg::this_grid();

@@ -101,19 +101,18 @@ def test_com_and_volume_are_bit_exact():
     d = H.config_test3d_cpp()
     h = _handle(d)
     _gpu_step(h, d, d["verts"], 1)
-    b = h.cell_bounds()  # bounds of the NEW positions; volume of the step's START positions
-    V0 = d["verts"].reshape(d["nc"], d["nv"], 4)
+    b = h.cell_bounds()  # per-cell scalars of the CURRENT (new) positions, produced by the step kernel's epilogue
+    V1, _ = h.download()
+    V1 = V1.reshape(d["nc"], d["nv"], 4)
     faces = d["faces"]
     for ci in range(d["nc"]):
         vol = np.float32(0)
         for f in faces:
-            P0, P1, P2 = V0[ci, f[0], :3], V0[ci, f[1], :3], V0[ci, f[2], :3]
+            P0, P1, P2 = V1[ci, f[0], :3], V1[ci, f[1], :3], V1[ci, f[2], :3]
             c = np.array([P0[1] * P1[2] - P0[2] * P1[1], P0[2] * P1[0] - P0[0] * P1[2], P0[0] * P1[1] - P0[1] * P1[0]], np.float32)
             t = np.float32(np.float32(np.float32(c[0] * P2[0]) + np.float32(c[1] * P2[1])) + np.float32(c[2] * P2[2]))
             vol = np.float32(vol + np.float32(t / np.float32(6.0)))
         assert np.float32(abs(vol)).tobytes() == b[ci, 11].tobytes(), (ci, vol, b[ci, 11])
-    V1, _ = h.download()
-    V1 = V1.reshape(d["nc"], d["nv"], 4)
     for ci in range(d["nc"]):
         s = np.zeros(3, np.float32)
         for i in range(d["nv"]):
