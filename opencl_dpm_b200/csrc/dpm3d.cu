@@ -37,7 +37,7 @@ int build_rings(int nv, int nf, const uint32_t *faces, std::vector<uint16_t> &ri
   int maxval = 0;
   for (int v = 0; v < nv; v++) maxval = std::max(maxval, (int)inc[v].size());
   if (maxval > 16) return fail(DPM_ERR_TOPOLOGY, "vertex valence > 16 is not supported");
-  stride = maxval;
+  stride = maxval <= 8 ? 8 : 16;  // 8 x uint16 = one 16-byte load per vertex in the step kernel
   ring_nbr.assign((size_t)nv * stride, 0);
   ring_face.assign((size_t)nv * stride, 0);
   valence.assign(nv, 0);
@@ -274,6 +274,10 @@ int dpm3d_create(dpm3d_t **out, int device, int ncells, int nv, int nf, const ui
   TRYB(cudaMalloc(&h->chunk_sum, sizeof(int) * h->coop_grid));
   rc = alloc_cand(h);
   if (rc) return bail(rc);
+  TRYB(cudaMalloc(&h->flag[0], (size_t)ncells * nf));
+  TRYB(cudaMalloc(&h->flag[1], (size_t)ncells * nf));
+  TRYB(cudaMalloc(&h->unit_idx, sizeof(unsigned) * nvert));
+  TRYB(cudaMemset(h->unit_idx, 0, sizeof(unsigned) * nvert));
   TRYB(cudaMalloc(&h->unit_base, sizeof(int) * ncells));
   TRYB(cudaMalloc(&h->unit_cnt, sizeof(int) * ncells));
   TRYB(cudaMemset(h->unit_cnt, 0, sizeof(int) * ncells));
@@ -298,7 +302,7 @@ int dpm3d_destroy(dpm3d_t *h) {
   shard_free(h);
   void *ptrs[] = {h->pos[0], h->pos[1], h->force, h->bnd[0], h->bnd[1], h->cellA, h->cellB, h->faces, h->ring_nbr, h->ring_face,
                   h->valence, h->face_adj, h->ring_tab, h->ring_end, h->dir_table, h->st, h->bbox_lo, h->bbox_hi, h->bin_id, h->order, h->bin_count, h->bin_start, h->cand_count,
-                  h->cand, h->partial, h->chunk_sum, h->unit_rec, h->unit_w, h->unit_base, h->unit_cnt};
+                  h->cand, h->partial, h->chunk_sum, h->unit_rec, h->unit_w, h->unit_base, h->unit_cnt, h->flag[0], h->flag[1], h->unit_idx};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (h->h_cell) cudaFreeHost(h->h_cell);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -364,7 +368,7 @@ static int upload_common(dpm3d_t *h, const float *verts4, bool on_device, const 
     DPM_CUDA_TRY(cudaMemcpyAsync(h->dir_table, tab.data(), sizeof(uint16_t) * tab.size(), cudaMemcpyHostToDevice, h->stream));
     DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
-  dpm3d_bounds_kernel<<<h->nc, STEP_THREADS, h->smem, h->stream>>>(h->pos[0], h->bnd[0], h->nc, cell_topo(h));
+  dpm3d_bounds_kernel<<<h->nc, STEP_THREADS, h->smem, h->stream>>>(h->pos[0], h->bnd[0], h->flag[0], h->nc, cell_topo(h));
   DPM_CUDA_TRY(cudaGetLastError());
   h->stats.launches += 1;
   h->stats.steps = 0; h->stats.rebuilds = 0; h->stats.contact_evals = 0;  // per-upload counters (launches stay cumulative)
@@ -410,6 +414,7 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
   p.face_adj = h->face_adj; p.ring_tab = h->ring_tab; p.ring_end = h->ring_end; p.dir_table = h->dir_table;
   p.cand_count = h->cand_count; p.cand = h->cand; p.K = h->K;
   p.bbox_lo = h->bbox_lo; p.bbox_hi = h->bbox_hi; p.st = h->st;
+  p.unit_idx = h->unit_idx;
   p.unit_rec = h->unit_rec; p.unit_w = h->unit_w; p.unit_base = h->unit_base; p.unit_cnt = h->unit_cnt; p.unit_cap = h->unit_cap;
   const bool repel = (h->mask & DPM3D_REPEL) && Kre != 0.0f;
   p.nc = h->nc; p.nv = h->nv; p.nf = h->nf; p.dt = dt; p.Kc = Kre; p.pbc = pbc; p.L = L; p.mask = h->mask;
@@ -427,6 +432,7 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
     DPM_CUDA_TRY(launch_rebuild(nbr_buffers(h, pbc, L), h->stream, h->coop_grid));
     p.pos_in = h->pos[h->cur]; p.pos_out = h->pos[h->cur ^ 1];
     p.bnd_in = h->bnd[h->cur]; p.bnd_out = h->bnd[h->cur ^ 1];
+    p.flag_in = h->flag[h->cur]; p.flag_out = h->flag[h->cur ^ 1];
     p.force_out = (s == nsteps - 1) ? h->force : nullptr;  // forces are only read back after the last step (:425-434)
     if (repel) {
       dpm3d_units_kernel<<<h->nc, UNITS_THREADS, 0, h->stream>>>(p);

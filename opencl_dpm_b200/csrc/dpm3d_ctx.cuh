@@ -27,6 +27,8 @@ struct dpm3d_ctx {
   uint8_t *ring_end = nullptr;
   uint16_t *dir_table = nullptr;   // rebuilt at every upload from cell 0
   std::vector<uint32_t> h_faces;
+  unsigned char *flag[2] = {nullptr, nullptr};  // per-face flags, ping-pong with pos/bnd
+  unsigned *unit_idx = nullptr;                 // per-vertex (offset << 8 | count) into the cell's unit range
   int2 *unit_rec = nullptr;  // contact-unit queue (dpm3d_units_kernel -> dpm3d_contact_kernel -> dpm3d_step_kernel)
   float *unit_w = nullptr;
   int *unit_base = nullptr, *unit_cnt = nullptr;

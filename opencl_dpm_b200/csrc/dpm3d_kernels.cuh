@@ -33,10 +33,13 @@ struct Step3DParams {
   const float4 *__restrict__ cellA;  // (Kv, Ka, Ks, v0)
   const float4 *__restrict__ cellB;  // (a0, l0, 0, 0)
   const ushort4 *__restrict__ faces;
-  const uint16_t *__restrict__ ring_nbr;
+  const uint16_t *__restrict__ ring_nbr;   // [nv][ring_stride], ring_stride == 8 (one 16-byte load per vertex) or 16
   const uint16_t *__restrict__ ring_face;
   const uint8_t *__restrict__ valence;
   int ring_stride;
+  const unsigned char *__restrict__ flag_in;  // [cell][nf] per-face flags of the CURRENT positions (bit0 facing the substrate,
+  unsigned char *__restrict__ flag_out;       //   bit1 degenerate edge), written by the previous epilogue / bounds kernel
+  unsigned *__restrict__ unit_idx;            // [vertex] (offset within the cell's unit range) << 8 | count
   const ushort4 *__restrict__ face_adj;    // face across edge (a,b), (b,c), (c,a)
   const uint16_t *__restrict__ ring_tab;   // per face: faces in BFS (edge-adjacency) order, RING_TAB entries
   const uint8_t *__restrict__ ring_end;    // per face: cumulative end of rings 0..RING_MAX
@@ -76,8 +79,8 @@ constexpr int BND = 4;              // float4 per cell in the bounds arrays:
 // box / sphere gets w_ref = W = 0 from it and is culled exactly.
 constexpr float CONTACT_PAD = 0.34f;
 constexpr float RANGE_HEADROOM = 1.25f;  // lists are built for pads up to 1.25x the largest current one
-constexpr int RING_MAX = 5;              // edge-adjacency rings examined around the radially hit face
-constexpr int RING_TAB = 48;             // 1 + 3 + 6 + 9 + 12 + 15 = 46 faces
+constexpr int RING_MAX = 7;              // edge-adjacency rings examined around the radially hit face
+constexpr int RING_TAB = 88;             // 1 + 3 + 6 + ... + 21 = 85 faces
 constexpr int DIR_N = 16;                // octahedral map resolution
 constexpr int MAX_WALK = 64;
 constexpr int UNIT_LANES = 8;            // lanes cooperating on one (vertex, neighbour) unit: ring faces / literal faces in parallel
@@ -303,10 +306,12 @@ static __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3
     return;
   }
   float4 myp[UNITS_VPT];
+  int cntj[UNITS_VPT];
   int cnt = 0;
 #pragma unroll
   for (int j = 0; j < UNITS_VPT; j++) {
     const int v = tid + j * UNITS_THREADS;
+    cntj[j] = 0;
     if (v < nv) {
       const float4 p = P.pos_in[(size_t)ci * nv + v];
       myp[j] = p;
@@ -314,9 +319,10 @@ static __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3
         if (sCand[k] < 0) continue;
         const float4 lo = sLo[k], hi = sHi[k], sp = sSph[k];
         const float dx = p.x - sp.x, dy = p.y - sp.y, dz = p.z - sp.z;
-        cnt += (!(p.x < lo.x || p.x > hi.x || p.y < lo.y || p.y > hi.y || p.z < lo.z || p.z > hi.z) &&
-                (dx * dx + dy * dy + dz * dz) <= sp.w) ? 1 : 0;
+        cntj[j] += (!(p.x < lo.x || p.x > hi.x || p.y < lo.y || p.y > hi.y || p.z < lo.z || p.z > hi.z) &&
+                    (dx * dx + dy * dy + dz * dz) <= sp.w) ? 1 : 0;
       }
+      cnt += cntj[j];
     }
   }
   // exclusive scan of the per-thread counts
@@ -340,6 +346,14 @@ static __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3
     P.unit_cnt[ci] = base < 0 ? 0 : total;
   }
   __syncthreads();
+  {  // per-vertex (offset, count) so that the step kernel finds a vertex's units without scanning
+    int off = woff + incl - cnt;
+#pragma unroll
+    for (int j = 0; j < UNITS_VPT; j++) {
+      const int v = tid + j * UNITS_THREADS;
+      if (v < nv) { P.unit_idx[(size_t)ci * nv + v] = ((unsigned)off << 8) | (unsigned)min(cntj[j], 255); off += cntj[j]; }
+    }
+  }
   if (total == 0 || sBase < 0) return;
   int2 *out = P.unit_rec + sBase + woff + incl - cnt;
 #pragma unroll
@@ -424,12 +438,27 @@ struct CellTopo {
 };
 
 __device__ __forceinline__ void cell_scalars(const float4 *sP, float *sTerm, const CellTopo &T, float vol_prev, float4 *bnd_cell,
-                                             const float4 *bbox_lo, const float4 *bbox_hi, NbrState *st) {
+                                             unsigned char *flag_cell, const float4 *bbox_lo, const float4 *bbox_hi, NbrState *st) {
   __shared__ float sRed[STEP_WARPS][10];
   __shared__ float sSc[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nv = T.nv, nf = T.nf;
-  // signed-volume terms dot(cross(P0,P1),P2)/6.0f, reference operation order, unfused (shaders/Cell3D_Kernel.cl:58-61)
+  // approximate centroid (tree sum): apex for the star-shape test only; the stored COM is the serial-order one
+  {
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int v = tid; v < nv; v += STEP_THREADS) { const float4 p = sP[v]; sx += p.x; sy += p.y; sz += p.z; }
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+    if (lane == 0) { sRed[warp][0] = sx; sRed[warp][1] = sy; sRed[warp][2] = sz; }
+  }
+  __syncthreads();
+  float3 capx = f3(0.f, 0.f, 0.f);
+  for (int w = 0; w < STEP_WARPS; w++) { capx.x += sRed[w][0]; capx.y += sRed[w][1]; capx.z += sRed[w][2]; }
+  capx = f3(capx.x / nv, capx.y / nv, capx.z / nv);
+  __syncthreads();
+  // ONE pass over the faces: signed-volume term dot(cross(P0,P1),P2)/6.0f in the reference's operation order, unfused
+  // (shaders/Cell3D_Kernel.cl:58-61); star-shape test; next step's facing-the-substrate (StickToSurface :209-214) and
+  // degenerate-edge (:151) flags
+  int star = 1;
   for (int f = tid; f < nf; f += STEP_THREADS) {
     const ushort4 fc = __ldg(T.faces + f);
     const float4 P0 = sP[fc.x], P1 = sP[fc.y], P2 = sP[fc.z];
@@ -437,6 +466,12 @@ __device__ __forceinline__ void cell_scalars(const float4 *sP, float *sTerm, con
     const float cy = __fsub_rn(__fmul_rn(P0.z, P1.x), __fmul_rn(P0.x, P1.z));
     const float cz = __fsub_rn(__fmul_rn(P0.x, P1.y), __fmul_rn(P0.y, P1.x));
     sTerm[f] = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, P2.x), __fmul_rn(cy, P2.y)), __fmul_rn(cz, P2.z)), 6.0f);
+    star &= face_sees_centre(P0, P1, P2, capx) ? 1 : 0;
+    const float3 A = sub3(P1, P0), B = sub3(P2, P0), C = sub3(P2, P1);
+    const float3 n = cross3(A, B);
+    const bool down = n.z * rsqrtf(dot3(n, n)) < -0.1f;
+    const bool deg = dot3(A, A) < 1e-24f || dot3(B, B) < 1e-24f || dot3(C, C) < 1e-24f;
+    flag_cell[f] = (unsigned char)((down ? 1 : 0) | (deg ? 2 : 0));
   }
   __syncthreads();
   if (warp == STEP_WARPS - 1) {  // serial volume chain (:46-64), every lane the same chain (broadcast LDS)
@@ -474,11 +509,6 @@ __device__ __forceinline__ void cell_scalars(const float4 *sP, float *sTerm, con
   const float3 com = f3(sSc[0], sSc[1], sSc[2]);
   float r2 = 0.0f, r2min = INFINITY;
   for (int v = tid; v < nv; v += STEP_THREADS) { const float3 q = sub3(sP[v], com); const float qq = dot3(q, q); r2 = fmaxf(r2, qq); r2min = fminf(r2min, qq); }
-  int star = 1;
-  for (int f = tid; f < nf; f += STEP_THREADS) {
-    const ushort4 fc = __ldg(T.faces + f);
-    star &= face_sees_centre(sP[fc.x], sP[fc.y], sP[fc.z], com) ? 1 : 0;
-  }
   r2 = warp_max(r2);
   r2min = warp_min(r2min);
   if (lane == 0) { sRed[warp][7] = r2; sRed[warp][8] = r2min; }
@@ -503,14 +533,15 @@ __device__ __forceinline__ void cell_scalars(const float4 *sP, float *sTerm, con
   }
 }
 
-static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_bounds_kernel(const float4 *pos, float4 *bnd, int nc, CellTopo T) {
+static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_bounds_kernel(const float4 *pos, float4 *bnd, unsigned char *flags, int nc,
+                                                                           CellTopo T) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 *sP = reinterpret_cast<float4 *>(smem_raw);
   float *sTerm = reinterpret_cast<float *>(sP + T.nv);
   const int ci = blockIdx.x;
   for (int v = threadIdx.x; v < T.nv; v += STEP_THREADS) sP[v] = pos[(size_t)ci * T.nv + v];
   __syncthreads();
-  cell_scalars(sP, sTerm, T, 0.0f, bnd + BND * (size_t)ci, nullptr, nullptr, nullptr);
+  cell_scalars(sP, sTerm, T, 0.0f, bnd + BND * (size_t)ci, flags + (size_t)ci * T.nf, nullptr, nullptr, nullptr);
 }
 
 // ---------------------------------------------------------------------------------
@@ -535,17 +566,11 @@ static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DP
 
   // ---- stage the vertex ring --------------------------------------------------------------------------
   for (int v = tid; v < nv; v += STEP_THREADS) sP[v] = gP[v];
-  __syncthreads();
 
-  // ---- per-face flags: facing the substrate (StickToSurface :209-214), degenerate edge (:151) ----------
-  for (int f = tid; f < nf; f += STEP_THREADS) {
-    const ushort4 fc = __ldg(P.faces + f);
-    const float4 P0 = sP[fc.x], P1 = sP[fc.y], P2 = sP[fc.z];
-    const float3 A = sub3(P1, P0), B = sub3(P2, P0), C = sub3(P2, P1);
-    const float3 n = cross3(A, B);
-    const bool down = n.z * rsqrtf(dot3(n, n)) < -0.1f;
-    const bool deg = dot3(A, A) < 1e-24f || dot3(B, B) < 1e-24f || dot3(C, C) < 1e-24f;
-    sFlag[f] = (unsigned char)((down ? 1 : 0) | (deg ? 2 : 0));
+  // ---- per-face flags of the current positions (computed by the previous epilogue) ------------------------
+  {
+    const unsigned char *gf = P.flag_in + (size_t)ci * nf;
+    for (int f = tid; f < nf; f += STEP_THREADS) sFlag[f] = gf[f];
   }
   __syncthreads();
 
@@ -561,20 +586,36 @@ static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DP
   const float scale = doArea ? Ka * sqrtf(a0) / l0 * 0.3f : 0.0f;  // :162
   const bool doRep = (P.mask & DPM3D_REPEL) && P.Kc != 0.0f;
   const int ucnt = doRep ? P.unit_cnt[ci] : 0;
-  const int2 *rec = P.unit_rec + (doRep ? P.unit_base[ci] : 0);
   const float *uw = P.unit_w + (doRep ? P.unit_base[ci] : 0);
 
   for (int v = tid; v < nv; v += STEP_THREADS) {
     const int val = __ldg(P.valence + v);
-    const uint16_t *rn = P.ring_nbr + (size_t)v * P.ring_stride;
-    const uint16_t *rf = P.ring_face + (size_t)v * P.ring_stride;
+    // ring tables: 8 x uint16 per vertex = one 16-byte load each (valence <= 8; the stride-16 layout takes two)
+    unsigned short rn[16], rf[16];
+    {
+      const uint4 a = __ldg(reinterpret_cast<const uint4 *>(P.ring_nbr + (size_t)v * P.ring_stride));
+      const uint4 b = __ldg(reinterpret_cast<const uint4 *>(P.ring_face + (size_t)v * P.ring_stride));
+      rn[0] = a.x & 0xffff; rn[1] = a.x >> 16; rn[2] = a.y & 0xffff; rn[3] = a.y >> 16; rn[4] = a.z & 0xffff; rn[5] = a.z >> 16; rn[6] = a.w & 0xffff; rn[7] = a.w >> 16;
+      rf[0] = b.x & 0xffff; rf[1] = b.x >> 16; rf[2] = b.y & 0xffff; rf[3] = b.y >> 16; rf[4] = b.z & 0xffff; rf[5] = b.z >> 16; rf[6] = b.w & 0xffff; rf[7] = b.w >> 16;
+      if (P.ring_stride > 8) {
+        const uint4 c = __ldg(reinterpret_cast<const uint4 *>(P.ring_nbr + (size_t)v * P.ring_stride) + 1);
+        const uint4 d = __ldg(reinterpret_cast<const uint4 *>(P.ring_face + (size_t)v * P.ring_stride) + 1);
+        rn[8] = c.x & 0xffff; rn[9] = c.x >> 16; rn[10] = c.y & 0xffff; rn[11] = c.y >> 16; rn[12] = c.z & 0xffff; rn[13] = c.z >> 16; rn[14] = c.w & 0xffff; rn[15] = c.w >> 16;
+        rf[8] = d.x & 0xffff; rf[9] = d.x >> 16; rf[10] = d.y & 0xffff; rf[11] = d.y >> 16; rf[12] = d.z & 0xffff; rf[13] = d.z >> 16; rf[14] = d.w & 0xffff; rf[15] = d.w >> 16;
+      }
+    }
     unsigned m = 0;
-    for (int i = 0; i < val; i++) m |= (unsigned)sFlag[__ldg(rf + i)] << (2 * i);
+#pragma unroll
+    for (int i = 0; i < 16; i++) if (i < val) m |= (unsigned)sFlag[rf[i]] << (2 * i);
     const int ndown = __popc(m & 0x55555555u);
     const float4 Pv = sP[v];
     float3 T = f3(0.f, 0.f, 0.f), g = f3(0.f, 0.f, 0.f), gs = f3(0.f, 0.f, 0.f), Qp = f3(0.f, 0.f, 0.f), Q0 = f3(0.f, 0.f, 0.f);
-    for (int i = 0; i < val; i++) {
-      const float4 Pn = sP[__ldg(rn + i)];
+    int rf_last = 0;  // ring face val-1 (tracked so that no local array is indexed dynamically)
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      if (i >= val) break;
+      rf_last = rf[i];
+      const float4 Pn = sP[rn[i]];
       const float3 E = sub3(Pn, Pv);
       const float len2 = dot3(E, E);
       const float rl = rsqrtf(len2);
@@ -589,14 +630,14 @@ static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DP
       else {
         const float3 c = cross3(Qp, Q);  // gradient of ring face i-1 = (v, n_{i-1}, n_i)
         g.x += c.x; g.y += c.y; g.z += c.z;
-        if (P.stale_from >= 0 && (int)__ldg(rf + i - 1) >= P.stale_from) { gs.x += c.x; gs.y += c.y; gs.z += c.z; }
+        if (P.stale_from >= 0 && (int)rf[i - 1] >= P.stale_from) { gs.x += c.x; gs.y += c.y; gs.z += c.z; }
       }
       Qp = Q;
     }
     {
       const float3 c = cross3(Qp, Q0);  // ring face val-1 = (v, n_{val-1}, n_0)
       g.x += c.x; g.y += c.y; g.z += c.z;
-      if (P.stale_from >= 0 && (int)__ldg(rf + val - 1) >= P.stale_from) { gs.x += c.x; gs.y += c.y; gs.z += c.z; }
+      if (P.stale_from >= 0 && rf_last >= P.stale_from) { gs.x += c.x; gs.y += c.y; gs.z += c.z; }
     }
     float3 F = f3(T.x * scale + coef * g.x + dcoef * gs.x, T.y * scale + coef * g.y + dcoef * gs.y, T.z * scale + coef * g.z + dcoef * gs.z);
     if (doStick && ndown > 0) {
@@ -612,22 +653,21 @@ static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DP
     }
     // fold this vertex's evaluated contact units (ordered by ascending neighbour id: the reference's cj order)
     if (ucnt > 0) {
-      const int gv = ci * nv + v;
+      const unsigned ui = P.unit_idx[(size_t)ci * nv + v];
+      const int un = ui & 0xffu, uo = ui >> 8;
       float3 dir = f3(0.f, 0.f, 0.f);
       bool have = false;
-      for (int u = 0; u < ucnt; u++) {
-        if (__ldg(&rec[u].x) == gv) {
-          const float wn = uw[u];
-          if (!(fabsf(wn) < 1e-6f)) {  // :302-308
-            if (!have) {
-              const float3 d = f3(com.x - Pv.x, com.y - Pv.y, com.z - Pv.z);
-              const float r = rsqrtf(dot3(d, d));
-              dir = f3(d.x * r, d.y * r, d.z * r);
-              have = true;
-            }
-            const float mg = fabsf(wn) * 0.5f * P.Kc;
-            F.x += mg * dir.x; F.y += mg * dir.y; F.z += mg * dir.z;
+      for (int u = uo; u < uo + un; u++) {
+        const float wn = uw[u];
+        if (!(fabsf(wn) < 1e-6f)) {  // :302-308
+          if (!have) {
+            const float3 d = f3(com.x - Pv.x, com.y - Pv.y, com.z - Pv.z);
+            const float r = rsqrtf(dot3(d, d));
+            dir = f3(d.x * r, d.y * r, d.z * r);
+            have = true;
           }
+          const float mg = fabsf(wn) * 0.5f * P.Kc;
+          F.x += mg * dir.x; F.y += mg * dir.y; F.z += mg * dir.z;
         }
       }
     }
@@ -650,7 +690,7 @@ static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DP
   // ---- next step's per-cell scalars from the NEW positions --------------------------------------------------
   CellTopo T;
   T.faces = P.faces; T.ring_nbr = P.ring_nbr; T.valence = P.valence; T.ring_stride = P.ring_stride; T.nv = nv; T.nf = nf;
-  cell_scalars(sP, sTerm, T, bi2.w, P.bnd_out + BND * (size_t)ci, P.bbox_lo + ci, P.bbox_hi + ci, P.st);
+  cell_scalars(sP, sTerm, T, bi2.w, P.bnd_out + BND * (size_t)ci, P.flag_out + (size_t)ci * nf, P.bbox_lo + ci, P.bbox_hi + ci, P.st);
 }
 
 }  // namespace dpm
