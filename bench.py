@@ -260,13 +260,13 @@ def main():
 
     # ---- device-resident throughput (`value`) -----------------------------------------------
     reset()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # started before the warm-up: nvidia-smi needs ~0.3 s before its first sample; all samples are under load
     for _ in range(args.warmup):
         run_steps(args.inner)
     torch.cuda.synchronize()
     launches0 = h.stats().launches
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
@@ -335,7 +335,8 @@ def main():
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "algorithmic_bytes_per_vertex_step": balg, "us_per_launch": t_launch * 1e6},
             "stats": {"rebuilds": int(st.rebuilds), "contact_evals_per_timestep": st.contact_evals / max(1, st.steps),
-                      "wall_s_timed_region": t_wall, "halo_bytes_per_timestep_rank0": st.halo_bytes / max(1, st.steps)},
+                      "wall_s_timed_region": t_wall, "halo_bytes_per_timestep_rank0": st.halo_bytes / max(1, st.steps),
+                      "literal_fallback_evals_per_timestep": st.reserved[0] / max(1, st.steps)},
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline_sample(d)
