@@ -53,40 +53,40 @@ struct Step2DParams {
 constexpr int T2D = 128;
 constexpr int W2D = T2D / 32;
 
-// literal even-odd test of RepulsionForceUpdate (:166-196) against a staged ring
-__device__ __forceinline__ bool inside2d(float2 p, const float2 *V, int nj, int pbc, float L) {
-  bool in = false;
-  float2 vj = V[nj - 1];
-  for (int i = 0; i < nj; i++) {
-    const float2 vi = V[i];
-    float dix = p.x - vi.x, diy = p.y - vi.y, djx = p.x - vj.x, djy = p.y - vj.y;
-    if (pbc) {
-      if (fabsf(dix) > L || fabsf(djx) > L) {
-        dix = __fsub_rn(dix, __fmul_rn(L, floorf(__fdiv_rn(dix, L))));
-        djx = __fsub_rn(djx, __fmul_rn(L, floorf(__fdiv_rn(djx, L))));
-      }
-      if (fabsf(diy) > L || fabsf(djy) > L) {
-        diy = __fsub_rn(diy, __fmul_rn(L, roundf(__fdiv_rn(diy, L))));
-        djy = __fsub_rn(djy, __fmul_rn(L, roundf(__fdiv_rn(djy, L))));
-      }
+// One edge (V[j] -> V[i]) of the literal even-odd test of RepulsionForceUpdate (:166-196): does it toggle "overlaps"?
+// `far` = a |d| > L wrap (the reference's floor/round quirk, :178-187) can fire for this vertex/cell pair at all.
+__device__ __forceinline__ bool edge_toggles(float2 p, float2 vi, float2 vj, bool far, float L) {
+  float dix = p.x - vi.x, diy = p.y - vi.y, djx = p.x - vj.x, djy = p.y - vj.y;
+  if (far) {
+    if (fabsf(dix) > L || fabsf(djx) > L) {
+      dix = __fsub_rn(dix, __fmul_rn(L, floorf(__fdiv_rn(dix, L))));
+      djx = __fsub_rn(djx, __fmul_rn(L, floorf(__fdiv_rn(djx, L))));
     }
-    if ((diy > 0.0f) != (djy > 0.0f)) {
-      const float xc = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(djx, dix), __fsub_rn(0.0f, diy)), __fsub_rn(djy, diy)), dix);
-      if (0.0f < xc) in = !in;
+    if (fabsf(diy) > L || fabsf(djy) > L) {
+      diy = __fsub_rn(diy, __fmul_rn(L, roundf(__fdiv_rn(diy, L))));
+      djy = __fsub_rn(djy, __fmul_rn(L, roundf(__fdiv_rn(djy, L))));
     }
-    vj = vi;
   }
-  return in;
+  if ((diy > 0.0f) == (djy > 0.0f)) return false;
+  const float xc = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(djx, dix), __fsub_rn(0.0f, diy)), __fsub_rn(djy, diy)), dix);
+  return 0.0f < xc;
 }
 
+// One warp per cell.  Shape forces are per-lane ring stencils; the two contact terms are evaluated WARP-COOPERATIVELY:
+// for every (vertex, candidate cell) pair that survives the exact culls, the 32 lanes split the candidate's ring —
+// edges of the even-odd test (parity of the ballots) and vertices of the attraction sum (nonzero terms folded in
+// ascending vertex order, the reference's order) — instead of each lane looping over the whole ring on its own.
 __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ci = blockIdx.x * W2D + warp;
   if (ci >= P.nc) return;  // whole warp leaves; no block-level barriers below
   const int S = P.S;
-  float2 *sV = reinterpret_cast<float2 *>(smem_raw) + (size_t)warp * 2 * S;
+  // per warp: own ring, staged neighbour ring, force accumulators, found flags
+  float2 *sV = reinterpret_cast<float2 *>(smem_raw) + (size_t)warp * 3 * S;
   float2 *sN = sV + S;
+  float2 *sF = sN + S;
+  unsigned char *sFound = reinterpret_cast<unsigned char *>(reinterpret_cast<float2 *>(smem_raw) + (size_t)W2D * 3 * S) + (size_t)warp * S;
   const int n = P.nv[ci];
   const float4 cA = P.cellA[ci], cB = P.cellB[ci];
   const float Ka = cA.x, Kl = cA.y, Kb = cA.z, a0 = cA.w, l0 = cB.x, r0 = cB.y;
@@ -110,31 +110,20 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
   if (area < 0.0f) area = -area;
   const float strain = __fsub_rn(__fdiv_rn(area, a0), 1.0f);  // :37
   const float comx = __fdiv_rn(sx, (float)n), comy = __fdiv_rn(sy, (float)n);
-  const float4 bi0 = P.bnd_in[3 * (size_t)ci], bi1 = P.bnd_in[3 * (size_t)ci + 1];
 
-  const int nchunk = (n + 31) >> 5;
-  const int ncand = min(P.cand_count[ci], P.K);
-  const bool doAtt = (P.mask & DPM2D_ATTRACT) && (P.Kat != 0.0f);  // Kat == 0 adds exact zeros in the reference
-  const bool doRep = (P.mask & DPM2D_REPEL);
-  const float halfL = 0.5f * P.L;
-  float lo[2] = {INFINITY, INFINITY}, hi[2] = {-INFINITY, -INFINITY};
-  unsigned long long evals = 0;
-
-  for (int ch = 0; ch < nchunk; ch++) {
-    const int vi = lane + 32 * ch;
-    const bool act = vi < n;
-    const int vc = act ? vi : 0;
-    const int im1 = (vc == 0) ? n - 1 : vc - 1, ip1 = (vc == n - 1) ? 0 : vc + 1;
+  // ---- shape forces: area (:38-41), perimeter (:109-118), bending (:73-89) -------------------------
+  for (int vi = lane; vi < n; vi += 32) {
+    const int im1 = (vi == 0) ? n - 1 : vi - 1, ip1 = (vi == n - 1) ? 0 : vi + 1;
     const int ip2 = (ip1 == n - 1) ? 0 : ip1 + 1, im2 = (im1 == 0) ? n - 1 : im1 - 1;
-    const float2 p = sV[vc], pm1 = sV[im1], pp1 = sV[ip1], pm2 = sV[im2], pp2 = sV[ip2];
+    const float2 p = sV[vi], pm1 = sV[im1], pp1 = sV[ip1], pm2 = sV[im2], pp2 = sV[ip2];
     float fx = 0.0f, fy = 0.0f;
     if (P.mask & DPM2D_AREA) {
-      const float c = (Ka / sqrtf(a0)) * 0.5f * strain;  // :38-41 (both components use im1 - ip1, sic)
+      const float c = (Ka / sqrtf(a0)) * 0.5f * strain;  // both components use im1 - ip1, sic
       fx += c * (pm1.y - pp1.y);
       fy += c * (pm1.x - pp1.x);
     }
     const float lvx = pp1.x - p.x, lvy = pp1.y - p.y, lmx = p.x - pm1.x, lmy = p.y - pm1.y;
-    if (P.mask & DPM2D_PERIMETER) {  // :109-118
+    if (P.mask & DPM2D_PERIMETER) {
       // edge strain len/l0 - 1 cancels to ~1e-2: keep the squared length unfused so it rounds like the reference's dot()
       const float len = sqrtf(__fadd_rn(__fmul_rn(lvx, lvx), __fmul_rn(lvy, lvy)));
       const float lenm = sqrtf(__fadd_rn(__fmul_rn(lmx, lmx), __fmul_rn(lmy, lmy)));
@@ -143,96 +132,152 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
       fx += k * (dli * (lvx / len) - dlim1 * (lmx / lenm));
       fy += k * (dli * (lvy / len) - dlim1 * (lmy / lenm));
     }
-    if (P.mask & DPM2D_BENDING) {  // :73-89
+    if (P.mask & DPM2D_BENDING) {
       const float six = lvx - lmx, siy = lvy - lmy;
       const float sixp = (pp2.x - pp1.x) - lvx, siyp = (pp2.y - pp1.y) - lvy;
       const float sixm = lmx - (pm1.x - pm2.x), siym = lmy - (pm1.y - pm2.y);
       fx += Kb * (2.0f * six - sixm - sixp);
       fy += Kb * (2.0f * siy - siym - siyp);
     }
+    sF[vi] = make_float2(fx, fy);
+    sFound[vi] = 0;
+  }
+  __syncwarp();
 
-    // ---- contacts: attraction (:250-267) and repulsion (:163-202) over the candidate cells ----
-    bool found = false;
-    if (doAtt || doRep) {
-      for (int k = 0; k < ncand; k++) {
-        const int cj = P.cand[(size_t)ci * P.K + k];
-        const float4 bj0 = P.bnd_in[3 * (size_t)cj], bj1 = P.bnd_in[3 * (size_t)cj + 1];
-        // per-vertex culls (exact): repulsion needs p inside AABB(cj) or a possible |d| > L wrap
-        bool wantRep = false, wantAtt = false;
-        if (act && doRep && !found) {
+  // ---- contacts: attraction (:250-267) and repulsion (:163-202) over the candidate cells, ascending id -----
+  const int nchunk = (n + 31) >> 5;
+  const int ncand = min(P.cand_count[ci], P.K);
+  const bool doAtt = (P.mask & DPM2D_ATTRACT) && (P.Kat != 0.0f);  // Kat == 0 adds exact zeros in the reference
+  const bool doRep = (P.mask & DPM2D_REPEL);
+  const float halfL = 0.5f * P.L;
+  unsigned evals = 0;
+  if (doAtt || doRep) {
+    for (int k = 0; k < ncand; k++) {
+      const int cj = P.cand[(size_t)ci * P.K + k];
+      const float4 bj0 = P.bnd_in[3 * (size_t)cj], bj1 = P.bnd_in[3 * (size_t)cj + 1];
+      const float hx = 0.5f * (bj1.x - bj0.x), hy = 0.5f * (bj1.y - bj0.y);
+      const float cxj = 0.5f * (bj0.x + bj1.x), cyj = 0.5f * (bj0.y + bj1.y);
+      const bool att_cull_ok = !P.pbc || ((hx + l0 < 0.25f * P.L) && (hy + l0 < 0.25f * P.L));
+      int nj = 0;
+      bool staged = false;
+      for (int ch = 0; ch < nchunk; ch++) {
+        const int vi = lane + 32 * ch;
+        const bool act = vi < n;
+        const float2 p = sV[act ? vi : 0];
+        // per-vertex culls (exact)
+        bool wantRep = false, far = false, wantAtt = false;
+        if (act && doRep && !sFound[vi]) {
           const float dxl = p.x - bj0.x, dxh = p.x - bj1.x, dyl = p.y - bj0.y, dyh = p.y - bj1.y;
           const bool inx = dxl >= 0.0f && dxh <= 0.0f, iny = dyl >= 0.0f && dyh <= 0.0f;
           const bool farx = P.pbc && (fabsf(dxl) > P.L || fabsf(dxh) > P.L), fary = P.pbc && (fabsf(dyl) > P.L || fabsf(dyh) > P.L);
           wantRep = (inx || farx) && (iny || fary);
+          far = farx || fary;
         }
         if (act && doAtt) {
-          const float hx = 0.5f * (bj1.x - bj0.x), hy = 0.5f * (bj1.y - bj0.y);
-          float dx = p.x - 0.5f * (bj0.x + bj1.x), dy = p.y - 0.5f * (bj0.y + bj1.y);
-          bool cull_ok = true;
-          if (P.pbc) {
-            cull_ok = (hx + l0 < 0.25f * P.L) && (hy + l0 < 0.25f * P.L);
-            dx -= P.L * roundf(dx / P.L);
-            dy -= P.L * roundf(dy / P.L);
-          }
+          float dx = p.x - cxj, dy = p.y - cyj;
+          if (P.pbc) { dx -= P.L * roundf(dx / P.L); dy -= P.L * roundf(dy / P.L); }
           const float ax = fmaxf(fabsf(dx) - hx, 0.0f), ay = fmaxf(fabsf(dy) - hy, 0.0f);
-          wantAtt = !cull_ok || (ax * ax + ay * ay <= l0 * l0 * 1.0001f + 1e-12f);
+          wantAtt = !att_cull_ok || (ax * ax + ay * ay <= l0 * l0 * 1.0001f + 1e-12f);
         }
-        if (!__any_sync(0xffffffffu, wantRep || wantAtt)) continue;
-        const int nj = P.nv[cj];
-        const float2 *gN = P.pos_in + (size_t)cj * S;
-        __syncwarp();
-        for (int v = lane; v < nj; v += 32) sN[v] = gN[v];
-        __syncwarp();
-        if (wantAtt) {
-          for (int vj = 0; vj < nj; vj++) {
-            const float2 q = sN[vj];
-            float rx = q.x - p.x, ry = q.y - p.y;
-            if (P.pbc) {  // rij -= L * round(rij / L)  (:254-256)
-              if (fabsf(rx) > halfL) rx -= P.L * roundf(rx / P.L);
-              if (fabsf(ry) > halfL) ry -= P.L * roundf(ry / P.L);
+        unsigned mAtt = __ballot_sync(0xffffffffu, wantAtt), mRep = __ballot_sync(0xffffffffu, wantRep);
+        const unsigned mFar = __ballot_sync(0xffffffffu, far);
+        if ((mAtt | mRep) == 0) continue;
+        if (!staged) {  // stage the neighbour's ring once per candidate
+          nj = P.nv[cj];
+          const float2 *gN = P.pos_in + (size_t)cj * S;
+          __syncwarp();
+          for (int v = lane; v < nj; v += 32) sN[v] = gN[v];
+          __syncwarp();
+          staged = true;
+        }
+        // attraction: lanes split the neighbour's vertices; nonzero terms are folded in ascending vertex order
+        while (mAtt) {
+          const int src = __ffs(mAtt) - 1;
+          mAtt &= mAtt - 1;
+          const float px = __shfl_sync(0xffffffffu, p.x, src), py = __shfl_sync(0xffffffffu, p.y, src);
+          float fx = 0.0f, fy = 0.0f;
+          bool any = false;
+          for (int base = 0; base < nj; base += 32) {
+            const int vj = base + lane;
+            float tx = 0.0f, ty = 0.0f;
+            bool hit = false;
+            if (vj < nj) {
+              const float2 q = sN[vj];
+              float rx = q.x - px, ry = q.y - py;
+              if (P.pbc) {  // rij -= L * round(rij / L)  (:254-256); a no-op unless |r| > L/2
+                if (fabsf(rx) > halfL) rx -= P.L * roundf(rx / P.L);
+                if (fabsf(ry) > halfL) ry -= P.L * roundf(ry / P.L);
+              }
+              const float dist = sqrtf(rx * rx + ry * ry);
+              if (dist < l0) {
+                const float ftmp = P.Kat / (float)n * dist / l0;  // :263
+                tx = ftmp * (rx / dist);
+                ty = ftmp * (ry / dist);
+                hit = true;
+              }
             }
-            const float d2 = rx * rx + ry * ry;
-            const float dist = sqrtf(d2);
-            if (dist < l0) {
-              const float ftmp = P.Kat / (float)n * dist / l0;  // :263
-              fx += ftmp * (rx / dist);
-              fy += ftmp * (ry / dist);
+            unsigned hm = __ballot_sync(0xffffffffu, hit);
+            while (hm) {
+              const int s2 = __ffs(hm) - 1;
+              hm &= hm - 1;
+              const float ax = __shfl_sync(0xffffffffu, tx, s2), ay = __shfl_sync(0xffffffffu, ty, s2);
+              if (!any) { const float2 f0 = sF[src + 32 * ch]; fx = f0.x; fy = f0.y; any = true; }
+              fx += ax; fy += ay;  // Forces[index] += ftmp * normalize(rij), in vj order (:264)
             }
           }
+          if (any && lane == 0) sF[src + 32 * ch] = make_float2(fx, fy);
+          __syncwarp();
         }
-        if (wantRep) {
-          found = inside2d(p, sN, nj, P.pbc, P.L);
+        // repulsion: lanes split the edges of the even-odd test; parity of all toggles
+        while (mRep) {
+          const int src = __ffs(mRep) - 1;
+          mRep &= mRep - 1;
+          const float2 pp = make_float2(__shfl_sync(0xffffffffu, p.x, src), __shfl_sync(0xffffffffu, p.y, src));
+          const bool ufar = (mFar >> src) & 1u;
+          unsigned par = 0;
+          for (int base = 0; base < nj; base += 32) {
+            const int i = base + lane;
+            bool tg = false;
+            if (i < nj) tg = edge_toggles(pp, sN[i], sN[i == 0 ? nj - 1 : i - 1], ufar, P.L);
+            par ^= __popc(__ballot_sync(0xffffffffu, tg));
+          }
+          if (lane == 0) sFound[src + 32 * ch] = (unsigned char)(par & 1u);
           evals++;
         }
+        __syncwarp();
       }
     }
-    if (found) {  // :204-218
+  }
+  __syncwarp();
+
+  // ---- repulsion force (:204-218), Euler (:279), bounds -----------------------------------------------
+  float lo[2] = {INFINITY, INFINITY}, hi[2] = {-INFINITY, -INFINITY};
+  for (int vi = lane; vi < n; vi += 32) {
+    const float2 p = sV[vi];
+    float2 f = sF[vi];
+    if (sFound[vi]) {
       float dx = comx - p.x, dy = comy - p.y;
       if (P.pbc) { dx -= P.L * roundf(dx / P.L); dy -= P.L * roundf(dy / P.L); }
       const float dist = sqrtf(dx * dx + dy * dy);
       const float xij = dist / (2.0f * r0);
       const float ftmp = P.Kre * (1.0f - xij);
-      fx += 0.5f * ftmp * (dx / dist);
-      fy += 0.5f * ftmp * (dy / dist);
+      f.x += 0.5f * ftmp * (dx / dist);
+      f.y += 0.5f * ftmp * (dy / dist);
     }
-    if (act) {
-      const float2 np = make_float2(p.x + fx * P.dt, p.y + fy * P.dt);  // EulerUpdate :279
-      P.pos_out[(size_t)ci * S + vi] = np;
-      if (P.force_out) P.force_out[(size_t)ci * S + vi] = make_float2(fx, fy);
-      lo[0] = fminf(lo[0], np.x); lo[1] = fminf(lo[1], np.y);
-      hi[0] = fmaxf(hi[0], np.x); hi[1] = fmaxf(hi[1], np.y);
-    }
+    const float2 np = make_float2(p.x + f.x * P.dt, p.y + f.y * P.dt);
+    P.pos_out[(size_t)ci * S + vi] = np;
+    if (P.force_out) P.force_out[(size_t)ci * S + vi] = f;
+    lo[0] = fminf(lo[0], np.x); lo[1] = fminf(lo[1], np.y);
+    hi[0] = fmaxf(hi[0], np.x); hi[1] = fmaxf(hi[1], np.y);
   }
-  (void)bi0; (void)bi1;
   for (int d = 0; d < 2; d++) { lo[d] = warp_min(lo[d]); hi[d] = warp_max(hi[d]); }
-  for (int o = 16; o > 0; o >>= 1) evals += __shfl_xor_sync(0xffffffffu, evals, o);
   if (lane == 0) {
     P.bnd_out[3 * (size_t)ci + 0] = make_float4(lo[0], lo[1], 0.f, 0.f);
     P.bnd_out[3 * (size_t)ci + 1] = make_float4(hi[0], hi[1], 0.f, 0.f);
     P.bnd_out[3 * (size_t)ci + 2] = make_float4(comx, comy, area, 0.f);
     const float4 bl = P.bbox_lo[ci], bh = P.bbox_hi[ci];
     if (lo[0] < bl.x || lo[1] < bl.y || hi[0] > bh.x || hi[1] > bh.y) P.st->rebuild = 1;
-    if (evals) atomicAdd(&P.st->contact_evals, evals);
+    if (evals) atomicAdd(&P.st->contact_evals, (unsigned long long)evals);
   }
 }
 
@@ -284,6 +329,9 @@ struct dpm2d_ctx {
 };
 
 namespace {
+// per warp: own ring, staged neighbour ring, force accumulators (float2 each) + found flags (bytes)
+inline size_t smem2d_bytes(int S) { return (sizeof(float2) * 3 + 1) * (size_t)S * W2D + 16; }
+
 struct DeviceGuard2 {
   int prev = -1;
   explicit DeviceGuard2(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
@@ -379,8 +427,7 @@ int dpm2d_create(dpm2d_t **out, int device, int ncells, int max_nv) {
   TRYB(cudaMalloc(&h->chunk_sum, sizeof(int) * h->coop_grid));
   int rc = alloc_cand2(h);
   if (rc) return bail(rc);
-  TRYB(cudaFuncSetAttribute(dpm2d_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(sizeof(float2) * 2 * max_nv * W2D)));
+  TRYB(cudaFuncSetAttribute(dpm2d_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2d_bytes(max_nv)));
 #undef TRYB
   *out = h;
   return DPM_OK;
@@ -483,7 +530,7 @@ int dpm2d_step(dpm2d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
   p.cand_count = h->cand_count; p.cand = h->cand; p.K = h->K;
   p.bbox_lo = h->bbox_lo; p.bbox_hi = h->bbox_hi; p.st = h->st;
   p.nc = h->nc; p.S = h->S; p.dt = dt; p.Kre = Kre; p.Kat = Kat; p.pbc = pbc; p.L = L; p.mask = h->mask;
-  const size_t smem = sizeof(float2) * 2 * h->S * W2D;
+  const size_t smem = smem2d_bytes(h->S);
   for (int s = 0; s < nsteps; s++) {
     DPM_CUDA_TRY(launch_rebuild(nbr_buffers2(h, range, pbc, L), h->stream, h->coop_grid));
     p.pos_in = h->pos[h->cur]; p.pos_out = h->pos[h->cur ^ 1];
