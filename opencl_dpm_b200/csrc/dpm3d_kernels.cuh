@@ -79,8 +79,8 @@ constexpr int BND = 4;              // float4 per cell in the bounds arrays:
 // box / sphere gets w_ref = W = 0 from it and is culled exactly.
 constexpr float CONTACT_PAD = 0.34f;
 constexpr float RANGE_HEADROOM = 1.25f;  // lists are built for pads up to 1.25x the largest current one
-constexpr int RING_MAX = 7;              // edge-adjacency rings examined around the radially hit face
-constexpr int RING_TAB = 88;             // 1 + 3 + 6 + ... + 21 = 85 faces
+constexpr int RING_MAX = 6;              // edge-adjacency rings examined around the radially hit face
+constexpr int RING_TAB = 64;             // 1 + 3 + 6 + 9 + 12 + 15 + 18 = 64 faces: one 64-bit hit mask
 constexpr int DIR_N = 16;                // octahedral map resolution
 constexpr int MAX_WALK = 64;
 constexpr int UNIT_LANES = 8;            // lanes cooperating on one (vertex, neighbour) unit: ring faces / literal faces in parallel
@@ -186,44 +186,63 @@ static __device__ __noinline__ float omega_skipped_f64(float3 a, float3 b, float
 
 // Returns 0 on success, else the reason the caller must fall back to the literal sum (1: vertex within the pad of
 // the neighbour's COM, 2: walk limit, 3: ring limit).
-__device__ __forceinline__ int winding_fast(const Step3DParams &P, const float4 *__restrict__ Vj, float4 sh, float4 p, float3 Cs,
-                                            float rho, float &w_out, int g, unsigned gmask) {
+// Warp-uniform version: the warp's 4 groups (UNIT_LANES = 8 lanes each) hold 4 different units and advance in
+// lockstep (every loop runs while ANY group needs it, idle groups are predicated off), so the heavy per-face math is
+// issued once for all four.  `active` = this lane's group has a unit.  Returns 0 on success, else the reason the
+// caller must fall back to the literal sum (1: vertex within the pad of the neighbour's COM, 2: walk limit,
+// 3: ring limit); group-uniform.
+__device__ __forceinline__ int winding_fast(const Step3DParams &P, bool active, const float4 *__restrict__ Vj, float4 sh, float4 p,
+                                            float3 Cs, float rho, float &w_out, int g, int gshift) {
+  const unsigned FULL = 0xffffffffu;
   const float3 u = f3(p.x - Cs.x, p.y - Cs.y, p.z - Cs.z);
   const float r2 = dot3(u, u);
-  if (!(r2 > 1.0201f * rho * rho)) return 1;
-  int f = __ldg(P.dir_table + octa_texel(u.x, u.y, u.z));
-  float3 A, B, C;
-  bool found = false;
+  int why = 0;
+  if (active && !(r2 > 1.0201f * rho * rho)) why = 1;
+  // ---- 1. walk to the face pierced by the ray C -> p ----------------------------------------------------
+  int f = (active && why == 0) ? (int)__ldg(P.dir_table + octa_texel(u.x, u.y, u.z)) : 0;
+  float3 A = f3(0.f, 0.f, 0.f), B = A, C = A;
+  bool found = !(active && why == 0);
   for (int it = 0; it < MAX_WALK; it++) {
-    const ushort4 fc = __ldg(P.faces + f);
-    const float4 q0 = __ldg(Vj + fc.x), q1 = __ldg(Vj + fc.y), q2 = __ldg(Vj + fc.z);
-    A = f3((q0.x + sh.x) - Cs.x, (q0.y + sh.y) - Cs.y, (q0.z + sh.z) - Cs.z);
-    B = f3((q1.x + sh.x) - Cs.x, (q1.y + sh.y) - Cs.y, (q1.z + sh.z) - Cs.z);
-    C = f3((q2.x + sh.x) - Cs.x, (q2.y + sh.y) - Cs.y, (q2.z + sh.z) - Cs.z);
-    const float d0 = dot3(u, cross3(A, B)), d1 = dot3(u, cross3(B, C)), d2 = dot3(u, cross3(C, A));
-    const float dm = fminf(d0, fminf(d1, d2));
-    if (dm >= 0.0f) { found = true; break; }
-    const ushort4 ad = __ldg(P.face_adj + f);
-    f = (dm == d0) ? ad.x : (dm == d1 ? ad.y : ad.z);
+    if (!__any_sync(FULL, !found)) break;
+    if (!found) {
+      const ushort4 fc = __ldg(P.faces + f);
+      const float4 q0 = __ldg(Vj + fc.x), q1 = __ldg(Vj + fc.y), q2 = __ldg(Vj + fc.z);
+      A = f3((q0.x + sh.x) - Cs.x, (q0.y + sh.y) - Cs.y, (q0.z + sh.z) - Cs.z);
+      B = f3((q1.x + sh.x) - Cs.x, (q1.y + sh.y) - Cs.y, (q1.z + sh.z) - Cs.z);
+      C = f3((q2.x + sh.x) - Cs.x, (q2.y + sh.y) - Cs.y, (q2.z + sh.z) - Cs.z);
+      const float d0 = dot3(u, cross3(A, B)), d1 = dot3(u, cross3(B, C)), d2 = dot3(u, cross3(C, A));
+      const float dm = fminf(d0, fminf(d1, d2));
+      if (dm >= 0.0f) found = true;
+      else {
+        const ushort4 ad = __ldg(P.face_adj + f);
+        f = (dm == d0) ? ad.x : (dm == d1 ? ad.y : ad.z);
+      }
+    }
   }
-  if (!found) return 2;
+  if (active && why == 0 && !found) why = 2;
+  bool open = active && why == 0;  // still examining rings
   // inside <=> p on the inner side of the hit face's plane (the COM is on the inner side of every face)
   const float3 n = cross3(f3(B.x - A.x, B.y - A.y, B.z - A.z), f3(C.x - A.x, C.y - A.y, C.z - A.z));
   const float W = (dot3(n, f3(u.x - A.x, u.y - A.y, u.z - A.z)) < 0.0f) ? 1.0f : 0.0f;
-  const float rinv = rsqrtf(r2);
-  const float sinp = rho * rinv;
+  const float sinp2 = open ? rho * rho / r2 : 0.0f;
+  const float s2 = sinp2 * r2 * 1.002f, c2 = (1.0f - sinp2) * r2 * 0.998f;
+  // ---- 2./3. rings of the hit face in chunks of UNIT_LANES table entries ----------------------------------
   const uint16_t *tab = P.ring_tab + (size_t)f * RING_TAB;
-  const uint8_t *rend = P.ring_end + (size_t)f * (RING_MAX + 1);
+  unsigned long long rends = 0;  // ring ends 0..RING_MAX packed, 8 bits each
+  if (open) {
+    const uint8_t *re = P.ring_end + (size_t)f * (RING_MAX + 1);
+#pragma unroll
+    for (int r = 0; r <= RING_MAX; r++) rends |= (unsigned long long)__ldg(re + r) << (8 * r);
+  }
   float corr = 0.0f;
-  int jbeg = 0;
-  bool open = true;  // the last examined ring still touched the cone
-  for (int ring = 0; ring <= RING_MAX && open; ring++) {  // uniform within the group: all its lanes hold the same unit
-    const int jend = __ldg(rend + ring);
-    unsigned touched = 0;
-    for (int base = jbeg; base < jend; base += UNIT_LANES) {
-      const int j = base + g;
-      bool hit = false;
-      if (j < jend) {
+  unsigned long long hits = 0;
+  int ring = 1;  // next ring whose completeness is checked (ring 0 = the hit face itself always touches the cone)
+  for (int base = 0; base < RING_TAB; base += UNIT_LANES) {
+    if (!__any_sync(FULL, open)) break;
+    const int j = base + g;
+    bool hit = false;
+    const int jlast = (int)((rends >> (8 * RING_MAX)) & 0xff);
+    if (open && j < jlast) {
       const int gf = __ldg(tab + j);
       const ushort4 gc = __ldg(P.faces + gf);
       const float4 q0 = __ldg(Vj + gc.x), q1 = __ldg(Vj + gc.y), q2 = __ldg(Vj + gc.z);
@@ -239,7 +258,6 @@ __device__ __forceinline__ int winding_fast(const Step3DParams &P, const float4 
       const float ab = dot3(ga, gb), bc = dot3(gb, gc2), ca = dot3(gc2, ga);
       const float3 n0 = cross3(ga, gb), n1 = cross3(gb, gc2), n2 = cross3(gc2, ga);
       const float e0 = dot3(u, n0), e1 = dot3(u, n1), e2 = dot3(u, n2);
-      const float s2 = sinp * sinp * r2 * 1.002f, c2 = (1.0f - sinp * sinp) * r2 * 0.998f;
       hit = (e0 >= 0.0f && e1 >= 0.0f && e2 >= 0.0f);
       hit = hit || (ua > 0.0f && ua * ua >= c2 * aa) || (ub > 0.0f && ub * ub >= c2 * bb) || (uc > 0.0f && uc * uc >= c2 * cc);
       hit = hit || (e0 < 0.0f && e0 * e0 <= s2 * dot3(n0, n0) && aa * ub - ab * ua >= 0.0f && ua * bb - ub * ab >= 0.0f);
@@ -250,15 +268,24 @@ __device__ __forceinline__ int winding_fast(const Step3DParams &P, const float4 
         solid_angle_terms(a, b, c, den, num);
         if (den < 1e-8f) corr += omega_skipped_f64(a, b, c);
       }
-      }
-      touched |= __ballot_sync(gmask, hit);
     }
-    open = touched != 0;
-    jbeg = jend;
+    const unsigned bal = __ballot_sync(FULL, hit);
+    hits |= (unsigned long long)((bal >> gshift) & 0xffu) << base;
+    // every ring that is now completely examined must have touched the cone, else the patch is closed
+    while (open && ring <= RING_MAX) {
+      const int rb = (int)((rends >> (8 * (ring - 1))) & 0xff), re2 = (int)((rends >> (8 * ring)) & 0xff);
+      if (re2 > base + UNIT_LANES) break;  // ring not completely examined yet
+      const unsigned long long rmask = (re2 >= 64 ? ~0ull : ((1ull << re2) - 1ull)) & ~((1ull << rb) - 1ull);
+      if ((hits & rmask) == 0ull) open = false;  // closed: nothing beyond this ring can touch the cone
+      else ring++;
+    }
+    if (open && ring > RING_MAX) { why = 3; open = false; }  // the outermost tabulated ring still touches the cone
   }
-  if (open) return 3;  // the outermost tabulated ring still touches the cone
-  w_out = W - group_sum(corr, gmask) / (4.0f * 3.14159274101257f);
-  return 0;
+  corr += __shfl_xor_sync(FULL, corr, 4);
+  corr += __shfl_xor_sync(FULL, corr, 2);
+  corr += __shfl_xor_sync(FULL, corr, 1);
+  w_out = W - corr / (4.0f * 3.14159274101257f);
+  return why;
 }
 
 // ---------------------------------------------------------------------------------
@@ -383,12 +410,18 @@ constexpr int CONTACT_THREADS = 256;
 static __global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(Step3DParams P) {
   const int lane = threadIdx.x & 31;
   const int g = lane & (UNIT_LANES - 1);
-  const unsigned gmask = ((1u << UNIT_LANES) - 1u) << (lane & ~(UNIT_LANES - 1));
+  const int gshift = lane & ~(UNIT_LANES - 1);
+  const unsigned gmask = ((1u << UNIT_LANES) - 1u) << gshift;
   const int ngroups = gridDim.x * (CONTACT_THREADS / UNIT_LANES);
   const int total = min(P.st->unit_total, P.unit_cap);
   const int nv = P.nv;
-  for (int u = blockIdx.x * (CONTACT_THREADS / UNIT_LANES) + threadIdx.x / UNIT_LANES; u < total; u += ngroups) {
-    const int2 rec = P.unit_rec[u];
+  // warp-uniform trip count: the 4 groups of a warp take 4 consecutive units and stay in lockstep
+  const int u0 = blockIdx.x * (CONTACT_THREADS / UNIT_LANES) + (threadIdx.x / 32) * (32 / UNIT_LANES);
+  for (int ub = u0; ub < total; ub += ngroups) {
+    const int u = ub + (lane / UNIT_LANES);
+    const bool active = u < total;
+    int2 rec = make_int2(0, 0);
+    if (active) rec = P.unit_rec[u];
     const int ci = rec.x / nv, cj = rec.y;
     const float4 p = P.pos_in[rec.x];
     const float4 bi2 = P.bnd_in[BND * (size_t)ci + 2];
@@ -400,14 +433,15 @@ static __global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(S
       sh.z = P.L * roundf((bi2.z - bj2.z) / P.L);
     }
     const float4 *Vj = P.pos_in + (size_t)cj * nv;
-    float w;
-    int why = -1;  // -1: neighbour not star-shaped about its COM
-    if (bj3.y != 0.0f) why = winding_fast(P, Vj, sh, p, f3(bj2.x + sh.x, bj2.y + sh.y, bj2.z + sh.z), bj1.w, w, g, gmask);
-    if (why != 0) {
+    const bool star = bj3.y != 0.0f;  // neighbour star-shaped about its COM (checked by its owner's epilogue)
+    float w = 0.0f;
+    int why = winding_fast(P, active && star, Vj, sh, p, f3(bj2.x + sh.x, bj2.y + sh.y, bj2.z + sh.z), bj1.w, w, g, gshift);
+    if (active && !star) why = -1;
+    if (active && why != 0) {  // group-uniform branch
       w = winding_literal(Vj, P.faces, P.nf, sh, p, g, gmask);
       if (g == 0) { atomicAdd(&P.st->literal_evals, 1ull); atomicAdd(&P.st->fallback_why[why < 0 ? 0 : why], 1ull); }
     }
-    if (g == 0) P.unit_w[u] = w;
+    if (active && g == 0) P.unit_w[u] = w;
   }
 }
 
