@@ -137,13 +137,16 @@ int pick_config(dpm3d_ctx *h) {
 size_t smem_for(dpm3d_ctx *h) { return step3d_smem_bytes(h->nv, h->nf); }
 
 cudaError_t set_smem(dpm3d_ctx *h) {
-  cudaError_t e = cudaFuncSetAttribute(dpm3d_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  cudaError_t e = cudaFuncSetAttribute(dpm3d_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(dpm3d_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(dpm3d_bounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
 }
 
 cudaError_t launch_step(dpm3d_ctx *h, const Step3DParams &p) {
-  dpm3d_step_kernel<<<p.nc, STEP_THREADS, h->smem, h->stream>>>(p);
+  if (h->ring_stride <= 8) dpm3d_step_kernel<8><<<p.nc, STEP_THREADS, h->smem, h->stream>>>(p);
+  else dpm3d_step_kernel<16><<<p.nc, STEP_THREADS, h->smem, h->stream>>>(p);
   return cudaGetLastError();
 }
 

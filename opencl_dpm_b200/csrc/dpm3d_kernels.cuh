@@ -103,6 +103,17 @@ __device__ __forceinline__ float3 cross3(float3 a, float3 b) {
   return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 
+// x / 6.0f, correctly rounded (== __fdiv_rn(x, 6.0f) for normal results): q0 = x * fl(1/6) is within 1 ulp, the
+// remainder r = x - 6 q0 is exact in an FMA, and q0 + r * fl(1/6) rounds to the correctly rounded quotient
+// (Markstein).  Results that are not comfortably normal take the IEEE division.
+__device__ __forceinline__ float div6_rn(float x) {
+  const float c = 0.16666667163372039794921875f;  // fl(1/6)
+  const float q0 = __fmul_rn(x, c);
+  const float r = __fmaf_rn(-6.0f, q0, x);
+  const float q1 = __fmaf_rn(r, c, q0);
+  return (fabsf(x) > 1e-30f && fabsf(x) < 1e30f) ? q1 : __fdiv_rn(x, 6.0f);
+}
+
 // Serial, individually rounded COM of nv float4 vertices in shared memory; lanes 0..2 each own
 // one component (shaders/Cell3D_Kernel.cl:35-44: sum in index order, then * 1/(float)NV).
 __device__ __forceinline__ float com_chain(const float4 *sP, int nv, int comp) {
@@ -493,18 +504,21 @@ __device__ __forceinline__ void cell_scalars(const float4 *sP, float *sTerm, con
   // (shaders/Cell3D_Kernel.cl:58-61); star-shape test; next step's facing-the-substrate (StickToSurface :209-214) and
   // degenerate-edge (:151) flags
   int star = 1;
+  float e2 = 0.0f;
   for (int f = tid; f < nf; f += STEP_THREADS) {
     const ushort4 fc = __ldg(T.faces + f);
     const float4 P0 = sP[fc.x], P1 = sP[fc.y], P2 = sP[fc.z];
     const float cx = __fsub_rn(__fmul_rn(P0.y, P1.z), __fmul_rn(P0.z, P1.y));
     const float cy = __fsub_rn(__fmul_rn(P0.z, P1.x), __fmul_rn(P0.x, P1.z));
     const float cz = __fsub_rn(__fmul_rn(P0.x, P1.y), __fmul_rn(P0.y, P1.x));
-    sTerm[f] = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, P2.x), __fmul_rn(cy, P2.y)), __fmul_rn(cz, P2.z)), 6.0f);
+    sTerm[f] = div6_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, P2.x), __fmul_rn(cy, P2.y)), __fmul_rn(cz, P2.z)));
     star &= face_sees_centre(P0, P1, P2, capx) ? 1 : 0;
     const float3 A = sub3(P1, P0), B = sub3(P2, P0), C = sub3(P2, P1);
     const float3 n = cross3(A, B);
     const bool down = n.z * rsqrtf(dot3(n, n)) < -0.1f;
-    const bool deg = dot3(A, A) < 1e-24f || dot3(B, B) < 1e-24f || dot3(C, C) < 1e-24f;
+    const float la = dot3(A, A), lb = dot3(B, B), lc = dot3(C, C);
+    e2 = fmaxf(e2, fmaxf(la, fmaxf(lb, lc)));  // every edge is an edge of some face: longest edge for free
+    const bool deg = la < 1e-24f || lb < 1e-24f || lc < 1e-24f;
     flag_cell[f] = (unsigned char)((down ? 1 : 0) | (deg ? 2 : 0));
   }
   __syncthreads();
@@ -523,17 +537,13 @@ __device__ __forceinline__ void cell_scalars(const float4 *sP, float *sTerm, con
   } else if (warp == STEP_WARPS - 2) {  // serial COM chain (:35-44), one lane per component
     if (lane < 3) sSc[lane] = com_chain(sP, nv, lane);
   }
-  // meanwhile (warps 0..): AABB and longest edge
+  // meanwhile (warps 0..): AABB
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  float e2 = 0.0f;
   if (warp < STEP_WARPS - 2) {
     for (int v = tid; v < nv; v += 32 * (STEP_WARPS - 2)) {
       const float4 p = sP[v];
       lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
       hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
-      const int val = __ldg(T.valence + v);
-      const uint16_t *rn = T.ring_nbr + (size_t)v * T.ring_stride;
-      for (int i = 0; i < val; i++) { const float3 e = sub3(sP[__ldg(rn + i)], p); e2 = fmaxf(e2, dot3(e, e)); }
     }
   }
   for (int d = 0; d < 3; d++) { lo[d] = warp_min(lo[d]); hi[d] = warp_max(hi[d]); }
@@ -583,7 +593,8 @@ static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_bounds_kernel(const
 // positions and force accumulators in shared memory (small register footprint -> 8+ CTAs per SM, which is what
 // hides the two serial chains of the epilogue).
 // ---------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DParams P) {
+template <int MAXV>  // ring-table stride: 8 (valence <= 8, the icospheres) or 16
+__global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nv = P.nv, nf = P.nf;
   float4 *sP = reinterpret_cast<float4 *>(smem_raw);
@@ -625,28 +636,30 @@ static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DP
   for (int v = tid; v < nv; v += STEP_THREADS) {
     const int val = __ldg(P.valence + v);
     // ring tables: 8 x uint16 per vertex = one 16-byte load each (valence <= 8; the stride-16 layout takes two)
-    unsigned short rn[16], rf[16];
+    unsigned short rn[MAXV], rf[MAXV];
     {
       const uint4 a = __ldg(reinterpret_cast<const uint4 *>(P.ring_nbr + (size_t)v * P.ring_stride));
       const uint4 b = __ldg(reinterpret_cast<const uint4 *>(P.ring_face + (size_t)v * P.ring_stride));
       rn[0] = a.x & 0xffff; rn[1] = a.x >> 16; rn[2] = a.y & 0xffff; rn[3] = a.y >> 16; rn[4] = a.z & 0xffff; rn[5] = a.z >> 16; rn[6] = a.w & 0xffff; rn[7] = a.w >> 16;
       rf[0] = b.x & 0xffff; rf[1] = b.x >> 16; rf[2] = b.y & 0xffff; rf[3] = b.y >> 16; rf[4] = b.z & 0xffff; rf[5] = b.z >> 16; rf[6] = b.w & 0xffff; rf[7] = b.w >> 16;
-      if (P.ring_stride > 8) {
+      if (MAXV > 8) {
         const uint4 c = __ldg(reinterpret_cast<const uint4 *>(P.ring_nbr + (size_t)v * P.ring_stride) + 1);
         const uint4 d = __ldg(reinterpret_cast<const uint4 *>(P.ring_face + (size_t)v * P.ring_stride) + 1);
-        rn[8] = c.x & 0xffff; rn[9] = c.x >> 16; rn[10] = c.y & 0xffff; rn[11] = c.y >> 16; rn[12] = c.z & 0xffff; rn[13] = c.z >> 16; rn[14] = c.w & 0xffff; rn[15] = c.w >> 16;
-        rf[8] = d.x & 0xffff; rf[9] = d.x >> 16; rf[10] = d.y & 0xffff; rf[11] = d.y >> 16; rf[12] = d.z & 0xffff; rf[13] = d.z >> 16; rf[14] = d.w & 0xffff; rf[15] = d.w >> 16;
+        rn[MAXV - 8] = c.x & 0xffff; rn[MAXV - 7] = c.x >> 16; rn[MAXV - 6] = c.y & 0xffff; rn[MAXV - 5] = c.y >> 16;
+        rn[MAXV - 4] = c.z & 0xffff; rn[MAXV - 3] = c.z >> 16; rn[MAXV - 2] = c.w & 0xffff; rn[MAXV - 1] = c.w >> 16;
+        rf[MAXV - 8] = d.x & 0xffff; rf[MAXV - 7] = d.x >> 16; rf[MAXV - 6] = d.y & 0xffff; rf[MAXV - 5] = d.y >> 16;
+        rf[MAXV - 4] = d.z & 0xffff; rf[MAXV - 3] = d.z >> 16; rf[MAXV - 2] = d.w & 0xffff; rf[MAXV - 1] = d.w >> 16;
       }
     }
     unsigned m = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) if (i < val) m |= (unsigned)sFlag[rf[i]] << (2 * i);
+    for (int i = 0; i < MAXV; i++) if (i < val) m |= (unsigned)sFlag[rf[i]] << (2 * i);
     const int ndown = __popc(m & 0x55555555u);
     const float4 Pv = sP[v];
     float3 T = f3(0.f, 0.f, 0.f), g = f3(0.f, 0.f, 0.f), gs = f3(0.f, 0.f, 0.f), Qp = f3(0.f, 0.f, 0.f), Q0 = f3(0.f, 0.f, 0.f);
     int rf_last = 0;  // ring face val-1 (tracked so that no local array is indexed dynamically)
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
+    for (int i = 0; i < MAXV; i++) {
       if (i >= val) break;
       rf_last = rf[i];
       const float4 Pn = sP[rn[i]];
