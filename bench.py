@@ -71,6 +71,21 @@ def make_workload(name: str, rank: int = 0, world: int = 1):
     return d
 
 
+class stdout_to_stderr:
+    """NCCL prints its version banner on fd 1 when the first communicator is created; the contract is ONE JSON line on
+    stdout, so fd 1 is pointed at stderr while communicators are set up."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks/throttle reasons while the timed region runs."""
 
@@ -187,10 +202,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    redirect = stdout_to_stderr()
+    redirect.__enter__()  # until the warm-up is done (NCCL communicators are created lazily)
     if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
     capi.lib()
     d = make_workload(args.workload, rank, world)
     dim = d["dim"]
@@ -266,6 +284,7 @@ def main():
     for _ in range(args.warmup):
         run_steps(args.inner)
     torch.cuda.synchronize()
+    redirect.__exit__()
     launches0 = h.stats().launches
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
