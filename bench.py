@@ -121,29 +121,47 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline_sample(d, budget_s: float = 20.0):
-    """The reference's ALL-PAIRS algorithm (oracle port, fp32, OpenMP over cells) on a bounded sample of
-    the same workload: forces for the first `ncells_sample` cells against all cells, one timestep."""
+def cpu_baseline_sample(d, budget_s: float = 20.0, allpairs: bool = True):
+    """CPU baseline on the box's host cores (oracle port, fp32, OpenMP), one timestep of forces.
+    allpairs=True : the reference's own ALL-PAIRS algorithm on a bounded sample — forces of the first k cells against
+                    all cells (cost per vertex is the same for every cell, so the sample's rate is the workload's rate);
+    allpairs=False: the same kernels behind the CPU restatement of the cell list (culled form, whole tissue) — the
+                    baseline BASELINE.md plans for configs B/D, where all-pairs takes hours per step."""
     from oracle import oracle as O
 
     cores = os.cpu_count() or 1
-    if d["dim"] == 3:
-        # all-pairs cost per sampled cell: nv * (nc-1) * nf face evaluations, ~1.4e8 face-evals/s on 8 cores
-        per_cell = d["nv"] * (d["nc"] - 1) * d["nf"] / (1.8e7 * cores)
+    if d["dim"] == 3 and allpairs:
+        per_cell = d["nv"] * (d["nc"] - 1) * d["nf"] / (1.7e7 * cores)
         ns = int(max(1, min(d["nc"], budget_s / max(per_cell, 1e-9))))
-        ns = min(ns, max(1, cores) * max(1, ns // max(1, cores)) if ns >= cores else ns)
         t0 = time.perf_counter()
         O.forces3d_range(d["verts"], d["faces"], *[d[k] for k in PK3], d["Kre"], d["PBC"], d["L"], 0, ns)
         dt = time.perf_counter() - t0
         nvert = ns * d["nv"]
-        sample = f"all-pairs forces of the first {ns} of {d['nc']} cells against all cells, 1 timestep ({dt:.1f} s)"
-    else:
-        ns = d["nc"]
+        sample = f"reference all-pairs algorithm: forces of the first {ns} of {d['nc']} cells against all cells, 1 timestep ({dt:.1f} s)"
+    elif d["dim"] == 3:
+        V = d["verts"].reshape(d["nc"], d["nv"], 4)
+        f = d["faces"]
+        emax = max(float(np.linalg.norm(V[:, f[:, i], :3] - V[:, f[:, (i + 1) % 3], :3], axis=2).max()) for i in range(3))
+        lo, hi = O.aabb3d(d["verts"], d["nc"])
         t0 = time.perf_counter()
-        O.forces2d(d["verts"], d["nv"], *[d[k] for k in PK2], d["Kre"], d["Kat"], d["PBC"], d["L"])
+        cl = O.cell_list(3, lo, hi, d["PBC"], d["L"], 0.1, 1.25 * 0.34 * emax, 32)
+        O.forces3d(d["verts"], d["faces"], *[d[k] for k in PK3], d["Kre"], d["PBC"], d["L"], cand_count=cl["cand_count"], cand=cl["cand"])
+        dt = time.perf_counter() - t0
+        nvert = d["nc"] * d["nv"]
+        sample = f"culled form (CPU cell list + literal kernels), all {d['nc']} cells, 1 timestep incl. list build ({dt:.1f} s)"
+    else:
+        t0 = time.perf_counter()
+        if allpairs:
+            O.forces2d(d["verts"], d["nv"], *[d[k] for k in PK2], d["Kre"], d["Kat"], d["PBC"], d["L"])
+            kind = "reference all-pairs algorithm"
+        else:
+            lo, hi = O.aabb2d(d["verts"], d["nv"])
+            cl = O.cell_list(2, lo, hi, d["PBC"], d["L"], 0.1, float(d["l0"].max()) if d["Kat"] != 0 else 0.0, 64, far2d=True)
+            O.forces2d(d["verts"], d["nv"], *[d[k] for k in PK2], d["Kre"], d["Kat"], d["PBC"], d["L"], cand_count=cl["cand_count"], cand=cl["cand"])
+            kind = "culled form (CPU cell list + literal kernels)"
         dt = time.perf_counter() - t0
         nvert = int(d["nv"].sum())
-        sample = f"all-pairs forces of all {ns} cells, 1 timestep ({dt:.1f} s)"
+        sample = f"{kind}, all {d['nc']} cells, 1 timestep ({dt:.1f} s)"
     return {"value": nvert / dt, "unit": "vertex-steps/s", "cores": cores, "kind": "port", "sample": sample}
 
 
@@ -160,12 +178,28 @@ def run_reference_arm(args):
             vals.append(cb["value"])
     v = float(np.mean(vals))
     cb["value"] = v
+    extra = {}
+    try:  # the REAL reference (its own host code + OpenCL kernels, oracle/_ref) when an OpenCL device is reachable
+        from oracle import ref as R
+
+        if R.available():
+            from opencl_dpm_b200 import synth
+
+            d64 = synth.monolayer3d(8, subdiv=2)
+            with stdout_to_stderr():  # the reference prints its own timing lines
+                _, _, sec = R.euler3d(d64["verts"], d64["Kv"], d64["Ka"], d64["Ks"], d64["v0"], d64["a0"], d64["Kre"], 1, d64["L"], 2, d64["dt"])
+            extra["reference_opencl"] = {
+                "device": R.device_name(), "workload": "64-cell monolayer x 162 vertices (the reference hard-codes NV=162), 2 timesteps, "
+                "whole CLEulerUpdate call incl. its per-call JIT build", "seconds": sec, "vertex_steps_per_s": 64 * 162 * 2 / sec,
+                "note": "all-pairs contact kernel: cost per vertex-step grows linearly with the cell count (x64 at 4096 cells)"}
+    except Exception as e:  # never let the informational leg break the arm
+        extra["reference_opencl"] = {"unavailable": str(e)[:200]}
     out = {"impl": "reference", "metric": "vertex-steps/sec (force+integrate)", "value": v, "unit": "vertex-steps/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "config": {"workload": d["desc"], "name": d["name"], "algorithm": "reference all-pairs (CPU port of the OpenCL kernels)"},
            "cpu_baseline": cb, "e2e": {"value": v, "unit": "vertex-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0}
+           "gpu_launches": 0, **extra}
     print(json.dumps(out), flush=True)
 
 
@@ -358,7 +392,8 @@ def main():
                       "literal_fallback_evals_per_timestep": st.reserved[0] / max(1, st.steps)},
         }
         if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_baseline_sample(d)
+            out["cpu_baseline"] = cpu_baseline_sample(d, allpairs=False)                  # same algorithmic complexity
+            out["cpu_baseline_reference_algorithm"] = cpu_baseline_sample(d, budget_s=12.0)  # the reference's all-pairs
         print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist

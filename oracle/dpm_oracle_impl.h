@@ -233,11 +233,11 @@ static void FN(forces3d_range)(int nc, int nv, int nf, const uint32_t *faces, co
     if (which & 4) FN(stick_force3d)(V, Fo, faces, nv, nf, Ks[ci], l0[ci]);
   }
   if ((which & 8) && Kc != (REAL)0.0) {
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for collapse(2) schedule(dynamic, 8)
     for (int ci = c0; ci < c1; ci++) {
-      const REAL *comi = coms + 3 * ci;
-      int ncand = cand ? cand_count[ci] : nc;
       for (int vi = 0; vi < nv; vi++) {
+        const REAL *comi = coms + 3 * ci;
+        int ncand = cand ? cand_count[ci] : nc;
         const REAL *p = verts + 4 * ((size_t)ci * nv + vi);
         REAL *fo = forces + 4 * ((size_t)ci * nv + vi);
         for (int k = 0; k < ncand; k++) {
