@@ -368,6 +368,12 @@ def main():
         n_step_kernels = args.inner * args.steps
         t_launch = ms * 1e-3 / n_step_kernels  # step-kernel launches dominate the region (the rebuild kernel is a no-op launch)
         achieved = nvert * balg / t_launch / 1e9  # per GPU: this rank's owned vertices per launch
+        traffic = None
+        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload, if any
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(d["name"], {}).get("bytes_per_launch")
+        except Exception:
+            pass
         out = {
             "metric": "vertex-steps/sec (force+integrate)", "value": value, "unit": "vertex-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -385,7 +391,7 @@ def main():
                     "ms_per_step": e2e_t * 1e3 / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "dpm3d_step_kernel" if dim == 3 else "dpm2d_step_kernel", "achieved": achieved,
-                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "algorithmic_bytes_per_vertex_step": balg, "us_per_launch": t_launch * 1e6},
             "stats": {"rebuilds": int(st.rebuilds), "contact_evals_per_timestep": st.contact_evals / max(1, st.steps),
                       "wall_s_timed_region": t_wall, "halo_bytes_per_timestep_rank0": st.halo_bytes / max(1, st.steps),

@@ -114,6 +114,31 @@ def run3d(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, nsteps, dt, which=1
     return V, Fo
 
 
+def run3d_culled(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, nsteps, dt, dtype=np.float32, rebuild_every=1):
+    """nsteps of the CULLED form (CPU cell list + literal kernels; equal to the all-pairs form, see the tests) — fast
+    enough for 1e4-step trajectories.  The candidate lists are rebuilt from the current fp32 AABBs every
+    `rebuild_every` steps with a generous margin."""
+    ct, sfx = _real(dtype)
+    faces = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+    nc = len(np.asarray(v0))
+    V = np.array(verts4, dtype=dtype, copy=True).reshape(-1, 4)
+    nv = V.shape[0] // nc
+    P = [_arr(x, nc, dtype) for x in (Kv, Ka, Ks, v0, a0, l0)]
+    Fo = np.zeros_like(V)
+    cl = None
+    for s in range(int(nsteps)):
+        if cl is None or s % rebuild_every == 0:
+            V32 = V.astype(np.float32)
+            lo, hi = aabb3d(V32, nc)
+            Vc = V32.reshape(nc, nv, 4)
+            emax = max(float(np.linalg.norm(Vc[:, faces[:, i], :3] - Vc[:, faces[:, (i + 1) % 3], :3], axis=2).max()) for i in range(3))
+            cl = cell_list(3, lo, hi, PBC, L, 0.3, 1.5 * 0.34 * emax, 64)
+            assert cl["cand_count"].max() <= 64
+        Fo = forces3d(V, faces, *P, Kc, PBC, L, cand_count=cl["cand_count"], cand=cl["cand"], dtype=dtype)
+        V[:, :3] += Fo[:, :3] * dtype(dt)
+    return V, Fo
+
+
 def aabb3d(verts4, nc):
     V = np.ascontiguousarray(verts4, np.float32).reshape(-1, 4)
     nv = V.shape[0] // nc

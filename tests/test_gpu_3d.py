@@ -94,6 +94,28 @@ def test_trajectory_100_steps_vs_oracle():
     h.close()
 
 
+def test_trajectory_10000_steps_vs_oracle():
+    """north_star: trajectories must stay within a stated tolerance over 1e4 steps.  reference test3D.cpp tissue (30
+    cells), 1e4 steps of dt 0.005: GPU vs the fp32 oracle (culled form, rebuilt every 5 steps with a wide margin) and the
+    oracle's own fp32-vs-fp64 drift.  Stated tolerance: 1e-3 of the tissue extent, and within 20x the oracle's own
+    precision drift."""
+    O = _oracle()
+    d = H.config_test3d_cpp()
+    h = _handle(d)
+    nsteps = 10000
+    V1, F1 = _gpu_step(h, d, d["verts"], nsteps)
+    args = (d["verts"], d["faces"], *[d[k] for k in PKEYS], d["Kre"], d["PBC"], d["L"], nsteps, d["dt"])
+    Vr, Fr = O.run3d_culled(*args, rebuild_every=5)
+    V64, _ = O.run3d_culled(*args, dtype=np.float64, rebuild_every=5)
+    scale = np.abs(Vr[:, :3]).max()
+    g = np.abs(V1[:, :3] - Vr[:, :3]).max() / scale
+    o = np.abs(Vr[:, :3] - V64[:, :3]).max() / scale
+    print(f"drift over {nsteps} steps: gpu-vs-f32 {g:.3e}  f32-vs-f64 {o:.3e}  (rebuilds on the GPU: {h.stats().rebuilds})")
+    assert np.isfinite(V1).all()
+    assert g <= max(1e-3, 20 * o)
+    h.close()
+
+
 def test_com_and_volume_are_bit_exact():
     """The two ill-conditioned per-cell sums are evaluated in the reference's serial order with
     individually rounded ops: COM and signed volume must equal the oracle's bit for bit."""
