@@ -8,6 +8,7 @@
 #include <map>
 #include <vector>
 
+#include <chrono>
 #include "dpm3d_ctx.cuh"
 
 using namespace dpm;
@@ -23,7 +24,7 @@ struct DeviceGuard {
 // Ring adjacency of a closed oriented 2-manifold: for vertex v the cyclic list n_0..n_{k-1}
 // such that ring face i is (v, n_i, n_{i+1}) in the mesh orientation.
 int build_rings(int nv, int nf, const uint32_t *faces, std::vector<uint16_t> &ring_nbr, std::vector<uint16_t> &ring_face,
-                std::vector<uint8_t> &valence, int &stride) {
+                std::vector<uint8_t> &valence, int &stride, int &minval, int &maxval) {
   std::vector<std::vector<std::array<uint32_t, 3>>> inc(nv);  // (next, nextnext, face)
   for (int f = 0; f < nf; f++) {
     for (int k = 0; k < 3; k++) {
@@ -34,8 +35,8 @@ int build_rings(int nv, int nf, const uint32_t *faces, std::vector<uint16_t> &ri
       inc[v].push_back({a, b, (uint32_t)f});
     }
   }
-  int maxval = 0;
-  for (int v = 0; v < nv; v++) maxval = std::max(maxval, (int)inc[v].size());
+  maxval = 0; minval = 1 << 30;
+  for (int v = 0; v < nv; v++) { maxval = std::max(maxval, (int)inc[v].size()); minval = std::min(minval, (int)inc[v].size()); }
   if (maxval > 16) return fail(DPM_ERR_TOPOLOGY, "vertex valence > 16 is not supported");
   stride = maxval <= 8 ? 8 : 16;  // 8 x uint16 = one 16-byte load per vertex in the step kernel
   ring_nbr.assign((size_t)nv * stride, 0);
@@ -99,34 +100,6 @@ void build_face_tables(int nf, const uint32_t *faces, std::vector<ushort4> &adj,
   }
 }
 
-// Walk-start guess: octahedral direction map -> face of cell 0 (about its centroid) containing that direction.
-void build_dir_table(int nv, int nf, const uint32_t *faces, const float *verts4_cell0, std::vector<uint16_t> &tab) {
-  double c[3] = {0, 0, 0};
-  for (int v = 0; v < nv; v++) for (int d = 0; d < 3; d++) c[d] += verts4_cell0[4 * v + d];
-  for (int d = 0; d < 3; d++) c[d] /= nv;
-  tab.assign(DIR_N * DIR_N, 0);
-  for (int iy = 0; iy < DIR_N; iy++)
-    for (int ix = 0; ix < DIR_N; ix++) {
-      double x = (ix + 0.5) / DIR_N * 2 - 1, y = (iy + 0.5) / DIR_N * 2 - 1, z = 1 - std::fabs(x) - std::fabs(y);
-      if (z < 0) { const double tx = (1 - std::fabs(y)) * (x >= 0 ? 1 : -1), ty = (1 - std::fabs(x)) * (y >= 0 ? 1 : -1); x = tx; y = ty; }
-      const double u[3] = {x, y, z};
-      int best = 0;
-      double bestv = -1e300;
-      for (int f = 0; f < nf; f++) {
-        double P[3][3];
-        for (int k = 0; k < 3; k++) for (int d = 0; d < 3; d++) P[k][d] = verts4_cell0[4 * faces[3 * f + k] + d] - c[d];
-        double m = 1e300;
-        for (int k = 0; k < 3; k++) {
-          const double *A = P[k], *B = P[(k + 1) % 3];
-          const double cr[3] = {A[1] * B[2] - A[2] * B[1], A[2] * B[0] - A[0] * B[2], A[0] * B[1] - A[1] * B[0]};
-          const double nrm = std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]) + 1e-300;
-          m = std::min(m, (u[0] * cr[0] + u[1] * cr[1] + u[2] * cr[2]) / nrm);
-        }
-        if (m > bestv) { bestv = m; best = f; }
-      }
-      tab[octa_texel((float)u[0], (float)u[1], (float)u[2])] = (uint16_t)best;
-    }
-}
 
 int pick_config(dpm3d_ctx *h) {
   if (h->nv > 1024) return fail(DPM_ERR_INVALID_ARGUMENT, "meshes with more than 1024 vertices per cell are not supported yet");
@@ -136,18 +109,32 @@ int pick_config(dpm3d_ctx *h) {
 
 size_t smem_for(dpm3d_ctx *h) { return step3d_smem_bytes(h->nv, h->nf); }
 
+// The step kernel variant for this mesh: ring slots read per vertex / slots every vertex has, and the compat mode.
+template <typename Fn>
+static cudaError_t with_step_kernel(dpm3d_ctx *h, Fn &&fn) {
+  const bool compat = h->stale_from >= 0;
+  if (h->ring_stride > 8) return compat ? fn(dpm3d_step_kernel<16, 3, true>) : fn(dpm3d_step_kernel<16, 3, false>);
+  if (h->min_valence >= 5 && h->max_valence <= 6) return compat ? fn(dpm3d_step_kernel<6, 5, true>) : fn(dpm3d_step_kernel<6, 5, false>);
+  return compat ? fn(dpm3d_step_kernel<8, 3, true>) : fn(dpm3d_step_kernel<8, 3, false>);
+}
+
 cudaError_t set_smem(dpm3d_ctx *h) {
-  cudaError_t e = cudaFuncSetAttribute(dpm3d_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(dpm3d_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(dpm3d_bounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  const int smem = (int)h->smem;
+  for (int compat = 0; compat < 2; compat++) {  // both modes: dpm3d_set_compat may be called at any time
+    const int keep = h->stale_from;
+    h->stale_from = compat ? 0 : -1;
+    cudaError_t e = with_step_kernel(h, [&](auto *k) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    h->stale_from = keep;
+    if (e != cudaSuccess) return e;
+  }
+  return cudaFuncSetAttribute(dpm3d_bounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 cudaError_t launch_step(dpm3d_ctx *h, const Step3DParams &p) {
-  if (h->ring_stride <= 8) dpm3d_step_kernel<8><<<p.nc, STEP_THREADS, h->smem, h->stream>>>(p);
-  else dpm3d_step_kernel<16><<<p.nc, STEP_THREADS, h->smem, h->stream>>>(p);
-  return cudaGetLastError();
+  return with_step_kernel(h, [&](auto *k) {
+    k<<<p.nc, STEP_THREADS, h->smem, h->stream>>>(p);
+    return cudaGetLastError();
+  });
 }
 
 CellTopo cell_topo(dpm3d_ctx *h) {
@@ -209,12 +196,13 @@ int dpm3d_create(dpm3d_t **out, int device, int ncells, int nv, int nf, const ui
   if (device < 0 || device >= ndev) return fail(DPM_ERR_CUDA, "no such CUDA device (there is no CPU fallback)");
   std::vector<uint16_t> rn, rf;
   std::vector<uint8_t> val;
-  int stride = 0;
-  int rc = build_rings(nv, nf, faces, rn, rf, val, stride);
+  int stride = 0, minval = 0, maxval = 0;
+  int rc = build_rings(nv, nf, faces, rn, rf, val, stride, minval, maxval);
   if (rc) return rc;
   DeviceGuard guard(device);
   dpm3d_ctx *h = new dpm3d_ctx();
   h->device = device; h->nc = ncells; h->nslots = ncells; h->nv = nv; h->nf = nf; h->ring_stride = stride;
+  h->min_valence = minval; h->max_valence = maxval;
   rc = pick_config(h);
   if (rc) { delete h; return rc; }
   auto bail = [&](int code) { dpm3d_destroy(h); return code; };
@@ -227,6 +215,7 @@ int dpm3d_create(dpm3d_t **out, int device, int ncells, int nv, int nf, const ui
   h->stream = h->own_stream;
   TRYB(cudaEventCreate(&h->ev0));
   TRYB(cudaEventCreate(&h->ev1));
+  TRYB(cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming));
   const size_t nvert = (size_t)ncells * nv;
   TRYB(cudaMalloc(&h->pos[0], sizeof(float4) * nvert));
   TRYB(cudaMalloc(&h->pos[1], sizeof(float4) * nvert));
@@ -310,6 +299,7 @@ int dpm3d_destroy(dpm3d_t *h) {
   if (h->h_cell) cudaFreeHost(h->h_cell);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_up) cudaEventDestroy(h->ev_up);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return DPM_OK;
@@ -349,9 +339,10 @@ int dpm3d_set_force_mask(dpm3d_t *h, unsigned mask) {
 }
 
 static int upload_common(dpm3d_t *h, const float *verts4, bool on_device, const float *Kv, const float *Ka, const float *Ks,
-                         const float *v0, const float *a0, const float *l0) {
+                         const float *v0, const float *a0, const float *l0, bool wait = true) {
   if (!h || !verts4 || !Kv || !Ka || !Ks || !v0 || !a0 || !l0) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL argument");
   DeviceGuard guard(h->device);
+  DPM_CUDA_TRY(cudaEventSynchronize(h->ev_up));  // the previous upload's copies out of the pinned staging buffer
   for (int c = 0; c < h->nc; c++) {
     h->h_cell[c] = make_float4(Kv[c], Ka[c], Ks[c], v0[c]);
     h->h_cell[h->nc + c] = make_float4(a0[c], l0[c], 0.f, 0.f);
@@ -362,15 +353,8 @@ static int upload_common(dpm3d_t *h, const float *verts4, bool on_device, const 
   DPM_CUDA_TRY(cudaMemcpyAsync(h->cellA, h->h_cell, sizeof(float4) * h->nc, cudaMemcpyHostToDevice, h->stream));
   DPM_CUDA_TRY(cudaMemcpyAsync(h->cellB, h->h_cell + h->nc, sizeof(float4) * h->nc, cudaMemcpyHostToDevice, h->stream));
   DPM_CUDA_TRY(cudaMemsetAsync(h->st, 0, sizeof(NbrState), h->stream));
-  {  // walk-start table of the fast contact evaluation, from cell 0's current shape
-    std::vector<float> cell0(4 * (size_t)h->nv);
-    if (on_device) DPM_CUDA_TRY(cudaMemcpy(cell0.data(), verts4, sizeof(float) * cell0.size(), cudaMemcpyDeviceToHost));
-    else memcpy(cell0.data(), verts4, sizeof(float) * cell0.size());
-    std::vector<uint16_t> tab;
-    build_dir_table(h->nv, h->nf, h->h_faces.data(), cell0.data(), tab);
-    DPM_CUDA_TRY(cudaMemcpyAsync(h->dir_table, tab.data(), sizeof(uint16_t) * tab.size(), cudaMemcpyHostToDevice, h->stream));
-    DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  }
+  // walk-start table of the fast contact evaluation, from cell 0's current shape
+  dpm3d_dirtable_kernel<<<DIR_N * DIR_N, STEP_THREADS, 0, h->stream>>>(h->pos[0], h->faces, h->nv, h->nf, h->dir_table);
   dpm3d_bounds_kernel<<<h->nc, STEP_THREADS, h->smem, h->stream>>>(h->pos[0], h->bnd[0], h->flag[0], h->nc, cell_topo(h));
   DPM_CUDA_TRY(cudaGetLastError());
   h->stats.launches += 1;
@@ -378,8 +362,10 @@ static int upload_common(dpm3d_t *h, const float *verts4, bool on_device, const 
   // mark the neighbour lists stale
   static const int one = 1;
   DPM_CUDA_TRY(cudaMemcpyAsync(&h->st->rebuild, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  // the pinned parameter staging buffer is reused by the next upload: wait for the copies
-  DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  // the pinned parameter staging buffer is reused by the next upload, which waits on this event; the caller's vertex
+  // array is borrowed until the call returns (euler_update keeps it until its download, so it does not wait here)
+  DPM_CUDA_TRY(cudaEventRecord(h->ev_up, h->stream));
+  if (wait && !on_device) DPM_CUDA_TRY(cudaEventSynchronize(h->ev_up));
   h->uploaded = true;
   return DPM_OK;
 }
@@ -494,17 +480,26 @@ int dpm3d_euler_update(dpm3d_t *h, float *verts4, float *forces4, const float *K
   if (nsteps <= 0) return fail(DPM_ERR_INVALID_ARGUMENT, "nsteps must be positive");
   if (!(dt > 0.0f) || dt > 0.1f) return fail(DPM_ERR_INVALID_ARGUMENT, "dt must be positive and reasonable");
   DeviceGuard guard(h->device);
+  static const bool trace = getenv("DPM_TRACE") != nullptr;  // host-side phase times of the call on stderr
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  auto ms_since = [&](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
+  double t_up = 0, t_enq = 0, t_run = 0;
   for (int attempt = 0;; attempt++) {
-    int rc = dpm3d_upload(h, verts4, Kv, Ka, Ks, v0, a0, l0);
+    int rc = upload_common(h, verts4, false, Kv, Ka, Ks, v0, a0, l0, /*wait=*/false);
     if (rc) return rc;
+    t_up = ms_since(t0);
     DPM_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     rc = dpm3d_step(h, nsteps, dt, Kre, Kat, pbc, L);
     if (rc) return rc;
     DPM_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    t_enq = ms_since(t0);
     rc = check_device_flags(h);
+    t_run = ms_since(t0);
     if (rc == DPM_ERR_RUNTIME && attempt < 3) {  // a capacity was exceeded: grow it and redo from the host state
       char msg[256];
       dpm_last_error(msg, sizeof msg);
+      if (trace) fprintf(stderr, "[dpm3d] euler_update attempt %d: %s -> growing\n", attempt, msg);
       if (strstr(msg, "contact unit")) {
         int rc2 = alloc_units(h, h->unit_per_cell * 4);
         if (rc2) return rc2;
@@ -520,7 +515,14 @@ int dpm3d_euler_update(dpm3d_t *h, float *verts4, float *forces4, const float *K
     break;
   }
   if (loop_ms) DPM_CUDA_TRY(cudaEventElapsedTime(loop_ms, h->ev0, h->ev1));
-  return dpm3d_download(h, verts4, forces4);
+  const int rc = dpm3d_download(h, verts4, forces4);
+  if (trace) {
+    float dev_ms = 0.f;
+    cudaEventElapsedTime(&dev_ms, h->ev0, h->ev1);
+    fprintf(stderr, "[dpm3d] euler_update %d steps: upload enqueued %.3f ms, steps enqueued %.3f, steps done %.3f (device loop %.3f), downloaded %.3f\n",
+            nsteps, t_up, t_enq, t_run, dev_ms, ms_since(t0));
+  }
+  return rc;
 }
 
 int dpm3d_get_neighbor_artifacts(dpm3d_t *h, dpm_grid_t *grid, int32_t *bin_id, int32_t *order, int32_t *bin_start,

@@ -21,7 +21,7 @@ struct dpm3d_ctx {
   ushort4 *faces = nullptr;
   uint16_t *ring_nbr = nullptr, *ring_face = nullptr;
   uint8_t *valence = nullptr;
-  int ring_stride = 0;
+  int ring_stride = 0, min_valence = 0, max_valence = 0;
   ushort4 *face_adj = nullptr;     // static topology tables of the fast contact evaluation (dpm3d_kernels.cuh)
   uint16_t *ring_tab = nullptr;
   uint8_t *ring_end = nullptr;
@@ -48,7 +48,7 @@ struct dpm3d_ctx {
   bool uploaded = false;
   int threads = 0, vpt = 0;
   size_t smem = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_up = nullptr;
   float4 *h_cell = nullptr;  // pinned staging for per-cell parameters
   dpm_stats_t stats{};
   int last_pbc = -1;

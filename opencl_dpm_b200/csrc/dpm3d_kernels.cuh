@@ -114,22 +114,43 @@ __device__ __forceinline__ float div6_rn(float x) {
   return (fabsf(x) > 1e-30f && fabsf(x) < 1e30f) ? q1 : __fdiv_rn(x, 6.0f);
 }
 
-// Serial, individually rounded COM of nv float4 vertices in shared memory; lanes 0..2 each own
-// one component (shaders/Cell3D_Kernel.cl:35-44: sum in index order, then * 1/(float)NV).
-__device__ __forceinline__ float com_chain(const float4 *sP, int nv, int comp) {
-  const float *base = reinterpret_cast<const float *>(sP) + comp;
-  float s = 0.0f;
-  int i = 0;
-  for (; i + 8 <= nv; i += 8) {
-    float t[8];
-#pragma unroll
-    for (int q = 0; q < 8; q++) t[q] = base[4 * (i + q)];
-#pragma unroll
-    for (int q = 0; q < 8; q++) s = __fadd_rn(s, t[q]);
-  }
-  for (; i < nv; i++) s = __fadd_rn(s, base[4 * i]);
-  return __fmul_rn(s, __fdiv_rn(1.0f, (float)nv));
+// 1/sqrt(x) as ONE MUFU.RSQ (rsqrtf() without -use_fast_math wraps it in denormal scaling: ~5 instructions);
+// identical to rsqrtf for normal x, which squared lengths of live edges are.
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
+
+// ---- 1-D bulk copies through the async proxy (TMA unit): one instruction moves a whole cell -------------------
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_%=;\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // octahedral direction -> texel of the DIR_N x DIR_N walk-start table (mirrored on the host in dpm3d.cu)
 __host__ __device__ inline int octa_texel(float x, float y, float z) {
@@ -456,20 +477,22 @@ static __global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(S
   }
 }
 
-// signed volume of the tetrahedron (C, P0, P1, P2) is positive with a margin for every face  <=>  the mesh is
-// star-shaped about C (closed, consistently oriented): the precondition of winding_fast
-__device__ __forceinline__ bool face_sees_centre(float4 P0, float4 P1, float4 P2, float3 C) {
-  const float3 a = sub3(P0, C), b = sub3(P1, C), c = sub3(P2, C);
-  const float3 cr = cross3(b, c);
-  const float sv = dot3(a, cr);
-  return sv > 0.0f && sv * sv > 1e-6f * dot3(a, a) * dot3(cr, cr);
+// signed volume of the tetrahedron (C, P0, P1, P2) = dot(P0 - C, n)/6, n = (P1-P0) x (P2-P0), is positive with a margin
+// (the sine of the angle between P0 - C and the face plane exceeds 1e-3) for every face  <=>  the mesh is star-shaped
+// about C (closed, consistently oriented): the precondition of winding_fast
+__device__ __forceinline__ bool face_sees_centre(float4 P0, float3 n, float nn, float3 C) {
+  const float3 a = sub3(P0, C);
+  const float sv = dot3(a, n);
+  return sv > 0.0f && sv * sv > 1e-6f * dot3(a, a) * nn;
 }
 
 // ---------------------------------------------------------------------------------
 // Per-cell scalars of the positions held in shared memory (sP): exact AABB, serial-order COM, serial-order signed
-// volume (both chains run CONCURRENTLY in two different warps), r^2 max/min about the COM, longest edge (-> contact
-// pad) and the star-shape flag.  Used by the bounds kernel (after an upload) and by the step kernel's epilogue (for
-// the NEW positions).  Block of STEP_THREADS threads; sTerm: nf floats of scratch.
+// volume (the four chains run in four lanes of ONE warp, rotated over the CTA's warps by the cell index so that every
+// SM sub-partition gets its share of them), r^2 max/min about the COM, longest edge (-> contact pad) and the
+// star-shape flag.  Used by the bounds kernel (after an upload) and by the step kernel's epilogue (for the NEW
+// positions).  Block of STEP_THREADS threads; sTerm: nf floats of scratch.  Every thread passes the partial vertex
+// sum and partial AABB of the vertices it staged / integrated (tid, tid + STEP_THREADS, ...).
 //   bnd[0] = (lo.xyz, r2max)   bnd[1] = (hi.xyz, pad)   bnd[2] = (com.xyz, volume)   bnd[3] = (r2min, star, vol_prev, 0)
 // ---------------------------------------------------------------------------------
 constexpr int STEP_THREADS = 128;
@@ -482,24 +505,48 @@ struct CellTopo {
   int ring_stride, nv, nf;
 };
 
-__device__ __forceinline__ void cell_scalars(const float4 *sP, float *sTerm, const CellTopo &T, float vol_prev, float4 *bnd_cell,
-                                             unsigned char *flag_cell, const float4 *bbox_lo, const float4 *bbox_hi, NbrState *st) {
-  __shared__ float sRed[STEP_WARPS][10];
+struct VertPartial {  // per-thread partials over the thread's own vertices
+  float sx, sy, sz;
+  float lo[3], hi[3];
+  __device__ __forceinline__ void init() {
+    sx = sy = sz = 0.0f;
+    lo[0] = lo[1] = lo[2] = INFINITY;
+    hi[0] = hi[1] = hi[2] = -INFINITY;
+  }
+  __device__ __forceinline__ void add(float4 p) {
+    sx += p.x; sy += p.y; sz += p.z;
+    lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+    hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+  }
+};
+
+__device__ __forceinline__ void cell_scalars(const float4 *sP, float *sTerm, const CellTopo &T, VertPartial vp, float vol_prev,
+                                             float4 *bnd_cell, unsigned char *flag_cell, const float4 *bbox_lo, const float4 *bbox_hi,
+                                             NbrState *st) {
+  __shared__ float sRed[STEP_WARPS][12];
   __shared__ float sSc[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nv = T.nv, nf = T.nf;
   // approximate centroid (tree sum): apex for the star-shape test only; the stored COM is the serial-order one
   {
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    for (int v = tid; v < nv; v += STEP_THREADS) { const float4 p = sP[v]; sx += p.x; sy += p.y; sz += p.z; }
-    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-    if (lane == 0) { sRed[warp][0] = sx; sRed[warp][1] = sy; sRed[warp][2] = sz; }
+    const float sx = warp_sum(vp.sx), sy = warp_sum(vp.sy), sz = warp_sum(vp.sz);
+    float lo[3], hi[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) { lo[d] = warp_min(vp.lo[d]); hi[d] = warp_max(vp.hi[d]); }
+    if (lane == 0) {
+      sRed[warp][0] = sx; sRed[warp][1] = sy; sRed[warp][2] = sz;
+#pragma unroll
+      for (int d = 0; d < 3; d++) { sRed[warp][3 + d] = lo[d]; sRed[warp][6 + d] = hi[d]; }
+    }
   }
   __syncthreads();
   float3 capx = f3(0.f, 0.f, 0.f);
+#pragma unroll
   for (int w = 0; w < STEP_WARPS; w++) { capx.x += sRed[w][0]; capx.y += sRed[w][1]; capx.z += sRed[w][2]; }
-  capx = f3(capx.x / nv, capx.y / nv, capx.z / nv);
-  __syncthreads();
+  {
+    const float inv = 1.0f / (float)nv;
+    capx = f3(capx.x * inv, capx.y * inv, capx.z * inv);
+  }
   // ONE pass over the faces: signed-volume term dot(cross(P0,P1),P2)/6.0f in the reference's operation order, unfused
   // (shaders/Cell3D_Kernel.cl:58-61); star-shape test; next step's facing-the-substrate (StickToSurface :209-214) and
   // degenerate-edge (:151) flags
@@ -512,57 +559,61 @@ __device__ __forceinline__ void cell_scalars(const float4 *sP, float *sTerm, con
     const float cy = __fsub_rn(__fmul_rn(P0.z, P1.x), __fmul_rn(P0.x, P1.z));
     const float cz = __fsub_rn(__fmul_rn(P0.x, P1.y), __fmul_rn(P0.y, P1.x));
     sTerm[f] = div6_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, P2.x), __fmul_rn(cy, P2.y)), __fmul_rn(cz, P2.z)));
-    star &= face_sees_centre(P0, P1, P2, capx) ? 1 : 0;
     const float3 A = sub3(P1, P0), B = sub3(P2, P0), C = sub3(P2, P1);
     const float3 n = cross3(A, B);
-    const bool down = n.z * rsqrtf(dot3(n, n)) < -0.1f;
+    const float nn = dot3(n, n);
+    star &= face_sees_centre(P0, n, nn, capx) ? 1 : 0;
+    const bool down = n.z * rsqrt_fast(nn) < -0.1f;
     const float la = dot3(A, A), lb = dot3(B, B), lc = dot3(C, C);
     e2 = fmaxf(e2, fmaxf(la, fmaxf(lb, lc)));  // every edge is an edge of some face: longest edge for free
-    const bool deg = la < 1e-24f || lb < 1e-24f || lc < 1e-24f;
+    const bool deg = fminf(la, fminf(lb, lc)) < 1e-24f;
     flag_cell[f] = (unsigned char)((down ? 1 : 0) | (deg ? 2 : 0));
   }
-  __syncthreads();
-  if (warp == STEP_WARPS - 1) {  // serial volume chain (:46-64), every lane the same chain (broadcast LDS)
-    float vol = 0.0f;
-    int f = 0;
-    for (; f + 8 <= nf; f += 8) {
-      float t[8];
-#pragma unroll
-      for (int q = 0; q < 8; q++) t[q] = sTerm[f + q];
-#pragma unroll
-      for (int q = 0; q < 8; q++) vol = __fadd_rn(vol, t[q]);
-    }
-    for (; f < nf; f++) vol = __fadd_rn(vol, sTerm[f]);
-    if (lane == 0) sSc[3] = fabsf(vol);
-  } else if (warp == STEP_WARPS - 2) {  // serial COM chain (:35-44), one lane per component
-    if (lane < 3) sSc[lane] = com_chain(sP, nv, lane);
-  }
-  // meanwhile (warps 0..): AABB
-  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  if (warp < STEP_WARPS - 2) {
-    for (int v = tid; v < nv; v += 32 * (STEP_WARPS - 2)) {
-      const float4 p = sP[v];
-      lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
-      hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
-    }
-  }
-  for (int d = 0; d < 3; d++) { lo[d] = warp_min(lo[d]); hi[d] = warp_max(hi[d]); }
   e2 = warp_max(e2);
-  if (lane == 0) { for (int d = 0; d < 3; d++) { sRed[warp][d] = lo[d]; sRed[warp][3 + d] = hi[d]; } sRed[warp][6] = e2; }
+  if (lane == 0) sRed[warp][9] = e2;
+  __syncthreads();
+  // The serial chains (:35-44 COM, :46-64 volume): lane 0/1/2 = COM x/y/z, lane 3 = signed volume.  Every iteration
+  // is one 8-byte LDS (lanes 0,1: sP[k].xy; lane 2: sP[k].zw; lane 3: terms 2k, 2k+1) and two predicated FADDs.
+  if (warp == (int)(blockIdx.x & (STEP_WARPS - 1)) && lane < 4) {
+    const float2 *src = (lane == 3) ? reinterpret_cast<const float2 *>(sTerm) : reinterpret_cast<const float2 *>(sP) + (lane == 2 ? 1 : 0);
+    const int stride = (lane == 3) ? 1 : 2;  // in float2
+    const bool useA = lane != 1, useB = (lane & 1) != 0;
+    const int cnt = (lane == 3) ? (nf >> 1) : nv;
+    const int ncommon = min(nv, nf >> 1);
+    float s = 0.0f;
+    int k = 0;
+    for (; k + 8 <= ncommon; k += 8) {
+      float2 t[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) t[q] = src[(k + q) * stride];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        if (useA) s = __fadd_rn(s, t[q].x);
+        if (useB) s = __fadd_rn(s, t[q].y);
+      }
+    }
+    for (; k < cnt; k++) {
+      const float2 t = src[k * stride];
+      if (useA) s = __fadd_rn(s, t.x);
+      if (useB) s = __fadd_rn(s, t.y);
+    }
+    if (lane == 3 && (nf & 1)) s = __fadd_rn(s, sTerm[nf - 1]);
+    sSc[lane] = (lane == 3) ? fabsf(s) : __fmul_rn(s, __fdiv_rn(1.0f, (float)nv));
+  }
   __syncthreads();
   const float3 com = f3(sSc[0], sSc[1], sSc[2]);
   float r2 = 0.0f, r2min = INFINITY;
   for (int v = tid; v < nv; v += STEP_THREADS) { const float3 q = sub3(sP[v], com); const float qq = dot3(q, q); r2 = fmaxf(r2, qq); r2min = fminf(r2min, qq); }
   r2 = warp_max(r2);
   r2min = warp_min(r2min);
-  if (lane == 0) { sRed[warp][7] = r2; sRed[warp][8] = r2min; }
+  if (lane == 0) { sRed[warp][10] = r2; sRed[warp][11] = r2min; }
   star = __syncthreads_and(star);
   if (tid == 0) {
     float l[3], h[3], em = 0.f, rr = 0.f, rm = INFINITY;
     for (int d = 0; d < 3; d++) { l[d] = INFINITY; h[d] = -INFINITY; }
     for (int w = 0; w < STEP_WARPS; w++) {
-      for (int d = 0; d < 3; d++) { l[d] = fminf(l[d], sRed[w][d]); h[d] = fmaxf(h[d], sRed[w][3 + d]); }
-      em = fmaxf(em, sRed[w][6]); rr = fmaxf(rr, sRed[w][7]); rm = fminf(rm, sRed[w][8]);
+      for (int d = 0; d < 3; d++) { l[d] = fminf(l[d], sRed[w][3 + d]); h[d] = fmaxf(h[d], sRed[w][6 + d]); }
+      em = fmaxf(em, sRed[w][9]); rr = fmaxf(rr, sRed[w][10]); rm = fminf(rm, sRed[w][11]);
     }
     const float pad = CONTACT_PAD * sqrtf(em);
     bnd_cell[0] = make_float4(l[0], l[1], l[2], rr);
@@ -581,21 +632,127 @@ static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_bounds_kernel(const
                                                                            CellTopo T) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 *sP = reinterpret_cast<float4 *>(smem_raw);
-  float *sTerm = reinterpret_cast<float *>(sP + T.nv);
+  float *sTerm = reinterpret_cast<float *>(sP + 2 * T.nv);  // same carve-up as the step kernel (sP, sF, sTerm, sFlag)
   const int ci = blockIdx.x;
-  for (int v = threadIdx.x; v < T.nv; v += STEP_THREADS) sP[v] = pos[(size_t)ci * T.nv + v];
+  VertPartial vp;
+  vp.init();
+  for (int v = threadIdx.x; v < T.nv; v += STEP_THREADS) {
+    const float4 p = pos[(size_t)ci * T.nv + v];
+    sP[v] = p;
+    vp.add(p);
+  }
   __syncthreads();
-  cell_scalars(sP, sTerm, T, 0.0f, bnd + BND * (size_t)ci, flags + (size_t)ci * T.nf, nullptr, nullptr, nullptr);
+  cell_scalars(sP, sTerm, T, vp, 0.0f, bnd + BND * (size_t)ci, flags + (size_t)ci * T.nf, nullptr, nullptr, nullptr);
+}
+
+// Walk-start table of the fast contact evaluation: for the direction of each octahedral texel, the face of cell 0 whose
+// spherical triangle (seen from the vertex mean) contains it best.  A hint only: the walk of winding_fast ends on the pierced
+// face from any start.  One CTA per texel, faces strided over the threads.
+static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_dirtable_kernel(const float4 *pos, const ushort4 *faces, int nv, int nf,
+                                                                             unsigned short *tab) {
+  __shared__ float sC[3][STEP_THREADS / 32];
+  __shared__ float sBestV[STEP_THREADS / 32];
+  __shared__ int sBestF[STEP_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float cx = 0.f, cy = 0.f, cz = 0.f;
+  for (int v = tid; v < nv; v += STEP_THREADS) { const float4 q = pos[v]; cx += q.x; cy += q.y; cz += q.z; }
+  cx = warp_sum(cx); cy = warp_sum(cy); cz = warp_sum(cz);
+  if (lane == 0) { sC[0][wid] = cx; sC[1][wid] = cy; sC[2][wid] = cz; }
+  __syncthreads();
+  cx = cy = cz = 0.f;
+  for (int w = 0; w < STEP_THREADS / 32; w++) { cx += sC[0][w]; cy += sC[1][w]; cz += sC[2][w]; }
+  const float inv = 1.0f / (float)nv;
+  const float3 c = f3(cx * inv, cy * inv, cz * inv);
+  const int ix = blockIdx.x % DIR_N, iy = blockIdx.x / DIR_N;
+  float x = (ix + 0.5f) / DIR_N * 2.0f - 1.0f, y = (iy + 0.5f) / DIR_N * 2.0f - 1.0f;
+  const float z = 1.0f - fabsf(x) - fabsf(y);
+  if (z < 0.0f) {
+    const float tx = (1.0f - fabsf(y)) * (x >= 0.0f ? 1.0f : -1.0f), ty = (1.0f - fabsf(x)) * (y >= 0.0f ? 1.0f : -1.0f);
+    x = tx; y = ty;
+  }
+  const float3 u = f3(x, y, z);
+  float bestv = -3.0e38f;
+  int best = 0;
+  for (int f = tid; f < nf; f += STEP_THREADS) {
+    const ushort4 fc = faces[f];
+    const float4 q0 = pos[fc.x], q1 = pos[fc.y], q2 = pos[fc.z];
+    const float3 A = f3(q0.x - c.x, q0.y - c.y, q0.z - c.z), B = f3(q1.x - c.x, q1.y - c.y, q1.z - c.z),
+                 C = f3(q2.x - c.x, q2.y - c.y, q2.z - c.z);
+    const float3 n0 = cross3(A, B), n1 = cross3(B, C), n2 = cross3(C, A);
+    const float m = fminf(dot3(u, n0) * rsqrtf(dot3(n0, n0) + 1e-30f),
+                          fminf(dot3(u, n1) * rsqrtf(dot3(n1, n1) + 1e-30f), dot3(u, n2) * rsqrtf(dot3(n2, n2) + 1e-30f)));
+    if (m > bestv) { bestv = m; best = f; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bestv, o);
+    const int of = __shfl_xor_sync(0xffffffffu, best, o);
+    if (ov > bestv || (ov == bestv && of < best)) { bestv = ov; best = of; }
+  }
+  if (lane == 0) { sBestV[wid] = bestv; sBestF[wid] = best; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < STEP_THREADS / 32; w++)
+      if (sBestV[w] > bestv || (sBestV[w] == bestv && sBestF[w] < best)) { bestv = sBestV[w]; best = sBestF[w]; }
+    tab[octa_texel(u.x, u.y, u.z)] = (unsigned short)best;
+  }
 }
 
 // ---------------------------------------------------------------------------------
 // K2: the fused shape-force + integrate kernel.  One CTA of 128 threads per cell, vertices strided over the threads,
-// positions and force accumulators in shared memory (small register footprint -> 8+ CTAs per SM, which is what
-// hides the two serial chains of the epilogue).
+// positions and force accumulators in shared memory (small register footprint -> 8 CTAs per SM, which is what
+// hides the serial chains of the epilogue).  The cell's positions and face flags arrive by two bulk async copies
+// (one instruction each), the new positions leave by one.
 // ---------------------------------------------------------------------------------
-template <int MAXV>  // ring-table stride: 8 (valence <= 8, the icospheres) or 16
+
+// Ring gather of one vertex: edge springs (SurfaceAreaForceUpdate :114-178) and the volume gradient (VolumeForceUpdate
+// :66-112).  DEG: some ring face of this warp's vertices has a degenerate edge (rare) -> per-edge weights; otherwise
+// every edge counts twice.  COMPAT: reference-race mode, the gradient is split by face index and taken about the COM
+// like the reference; otherwise it is taken about the vertex itself (same sum over a closed ring, smaller terms).
+template <int MAXV, int MINV, bool DEG, bool COMPAT>
+__device__ __forceinline__ void ring_gather(const float4 *sP, const unsigned short (&rn)[MAXV], const unsigned short (&rf)[MAXV], int val,
+                                            unsigned m, float4 Pv, float3 com, float inv_l0, int stale_from, float3 &T, float3 &g,
+                                            float3 &gs) {
+  float3 Qp = f3(0.f, 0.f, 0.f), Q0 = f3(0.f, 0.f, 0.f);
+  int rf_last = 0;  // ring face val-1 (tracked so that no local array is indexed dynamically)
+#pragma unroll
+  for (int i = 0; i < MAXV; i++) {
+    if (i >= MINV && i >= val) break;
+    rf_last = rf[i];
+    const float4 Pn = sP[rn[i]];
+    const float3 E = sub3(Pn, Pv);
+    const float len2 = dot3(E, E);
+    const float rl = rsqrt_fast(len2);
+    const float dl = len2 * rl * inv_l0 - 1.0f;  // len/l0 - 1  (:156-160)
+    float sc = rl * dl;
+    if (DEG) {
+      // edge (v, n_i) belongs to ring faces i-1 and i; each contributes unit(E)*dl unless degenerate
+      const int ip = (i == 0) ? val - 1 : i - 1;
+      sc *= (float)(2 - ((m >> (2 * i + 1)) & 1u) - ((m >> (2 * ip + 1)) & 1u));
+    }
+    T.x += E.x * sc; T.y += E.y * sc; T.z += E.z * sc;
+    const float3 Q = COMPAT ? sub3(Pn, com) : E;
+    if (i == 0) Q0 = Q;
+    else {
+      const float3 c = cross3(Qp, Q);  // gradient of ring face i-1 = (v, n_{i-1}, n_i)
+      g.x += c.x; g.y += c.y; g.z += c.z;
+      if (COMPAT && (int)rf[i - 1] >= stale_from) { gs.x += c.x; gs.y += c.y; gs.z += c.z; }
+    }
+    Qp = Q;
+  }
+  {
+    const float3 c = cross3(Qp, Q0);  // ring face val-1 = (v, n_{val-1}, n_0)
+    g.x += c.x; g.y += c.y; g.z += c.z;
+    if (COMPAT && rf_last >= stale_from) { gs.x += c.x; gs.y += c.y; gs.z += c.z; }
+  }
+  if (!DEG) { T.x *= 2.0f; T.y *= 2.0f; T.z *= 2.0f; }
+}
+
+// MAXV: ring slots read per vertex (6: valence 5..6, the icospheres; 8; 16 = two 16-byte loads); MINV: ring slots
+// known to be occupied for every vertex (no bound check)
+template <int MAXV, int MINV, bool COMPAT>
 __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long sBar;
   const int nv = P.nv, nf = P.nf;
   float4 *sP = reinterpret_cast<float4 *>(smem_raw);
   float4 *sF = sP + nv;
@@ -603,28 +760,29 @@ __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DParams P
   unsigned char *sFlag = reinterpret_cast<unsigned char *>(sTerm + nf);
   const int tid = threadIdx.x;
   const int ci = blockIdx.x;
+  const float4 *gP = P.pos_in + (size_t)ci * nv;
+  const unsigned char *gf = P.flag_in + (size_t)ci * nf;
+
+  // ---- stage the vertex ring and the per-face flags of the current positions (computed by the previous epilogue) ----
+  const bool bulk_flags = (nf & 15) == 0;  // bulk copies move multiples of 16 bytes between 16-byte aligned addresses
+  if (tid == 0) {
+    mbar_init(&sBar, 1);
+    const unsigned pb = (unsigned)(sizeof(float4) * nv), fb = bulk_flags ? (unsigned)nf : 0u;
+    mbar_expect_tx(&sBar, pb + fb);
+    bulk_g2s(sP, gP, pb, &sBar);
+    if (bulk_flags) bulk_g2s(sFlag, gf, fb, &sBar);
+  }
+  if (!bulk_flags)
+    for (int f = tid; f < nf; f += STEP_THREADS) sFlag[f] = gf[f];
   const float4 cA = P.cellA[ci], cB = P.cellB[ci];
   const float Kv = cA.x, Ka = cA.y, Ks = cA.z, v0 = cA.w, a0 = cB.x, l0 = cB.y;
   const float4 bi2 = P.bnd_in[BND * (size_t)ci + 2], bi3 = P.bnd_in[BND * (size_t)ci + 3];
   const float3 com = f3(bi2.x, bi2.y, bi2.z);
-  const float4 *gP = P.pos_in + (size_t)ci * nv;
-
-  // ---- stage the vertex ring --------------------------------------------------------------------------
-  for (int v = tid; v < nv; v += STEP_THREADS) sP[v] = gP[v];
-
-  // ---- per-face flags of the current positions (computed by the previous epilogue) ------------------------
-  {
-    const unsigned char *gf = P.flag_in + (size_t)ci * nf;
-    for (int f = tid; f < nf; f += STEP_THREADS) sFlag[f] = gf[f];
-  }
-  __syncthreads();
-
-  // ---- ring pass: every vertex gathers over its constant ring adjacency ---------------------------------
   const bool doVol = (P.mask & DPM3D_VOLUME) && (Kv != 0.0f);
   // volume of the CURRENT positions was left in the bounds by the previous epilogue (serial-order chain)
   const float coef = doVol ? (-Kv * (bi2.w / v0 - 1.0f)) * (1.0f / 6.0f) : 0.0f;  // :85,:106-108
   // compat mode: faces >= stale_from see the volume of the previous step's start (0 right after an upload)
-  const float dcoef = (doVol && P.stale_from >= 0) ? (-Kv * (bi3.z / v0 - 1.0f)) * (1.0f / 6.0f) - coef : 0.0f;
+  const float dcoef = (COMPAT && doVol) ? (-Kv * (bi3.z / v0 - 1.0f)) * (1.0f / 6.0f) - coef : 0.0f;
   const bool doArea = (P.mask & DPM3D_AREA) && !(Ka < 1e-8f);
   const bool doStick = (P.mask & DPM3D_STICK) && !(Ks < 1e-12f);
   const float inv_l0 = 1.0f / l0;
@@ -632,16 +790,20 @@ __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DParams P
   const bool doRep = (P.mask & DPM3D_REPEL) && P.Kc != 0.0f;
   const int ucnt = doRep ? P.unit_cnt[ci] : 0;
   const float *uw = P.unit_w + (doRep ? P.unit_base[ci] : 0);
+  __syncthreads();  // the barrier is initialised (and the plain flag copy, if any, is complete)
+  mbar_wait(&sBar, 0);
 
+  // ---- ring pass: every vertex gathers over its constant ring adjacency ---------------------------------
   for (int v = tid; v < nv; v += STEP_THREADS) {
-    const int val = __ldg(P.valence + v);
+    const int val = (MINV == MAXV) ? MAXV : (int)__ldg(P.valence + v);
     // ring tables: 8 x uint16 per vertex = one 16-byte load each (valence <= 8; the stride-16 layout takes two)
     unsigned short rn[MAXV], rf[MAXV];
     {
       const uint4 a = __ldg(reinterpret_cast<const uint4 *>(P.ring_nbr + (size_t)v * P.ring_stride));
       const uint4 b = __ldg(reinterpret_cast<const uint4 *>(P.ring_face + (size_t)v * P.ring_stride));
-      rn[0] = a.x & 0xffff; rn[1] = a.x >> 16; rn[2] = a.y & 0xffff; rn[3] = a.y >> 16; rn[4] = a.z & 0xffff; rn[5] = a.z >> 16; rn[6] = a.w & 0xffff; rn[7] = a.w >> 16;
-      rf[0] = b.x & 0xffff; rf[1] = b.x >> 16; rf[2] = b.y & 0xffff; rf[3] = b.y >> 16; rf[4] = b.z & 0xffff; rf[5] = b.z >> 16; rf[6] = b.w & 0xffff; rf[7] = b.w >> 16;
+      rn[0] = a.x & 0xffff; rn[1] = a.x >> 16; rn[2] = a.y & 0xffff; rn[3] = a.y >> 16; rn[4] = a.z & 0xffff; rn[5] = a.z >> 16;
+      rf[0] = b.x & 0xffff; rf[1] = b.x >> 16; rf[2] = b.y & 0xffff; rf[3] = b.y >> 16; rf[4] = b.z & 0xffff; rf[5] = b.z >> 16;
+      if (MAXV > 6) { rn[6] = a.w & 0xffff; rn[7] = a.w >> 16; rf[6] = b.w & 0xffff; rf[7] = b.w >> 16; }
       if (MAXV > 8) {
         const uint4 c = __ldg(reinterpret_cast<const uint4 *>(P.ring_nbr + (size_t)v * P.ring_stride) + 1);
         const uint4 d = __ldg(reinterpret_cast<const uint4 *>(P.ring_face + (size_t)v * P.ring_stride) + 1);
@@ -653,48 +815,24 @@ __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DParams P
     }
     unsigned m = 0;
 #pragma unroll
-    for (int i = 0; i < MAXV; i++) if (i < val) m |= (unsigned)sFlag[rf[i]] << (2 * i);
+    for (int i = 0; i < MAXV; i++) if (i < MINV || i < val) m |= (unsigned)sFlag[rf[i]] << (2 * i);
     const int ndown = __popc(m & 0x55555555u);
     const float4 Pv = sP[v];
-    float3 T = f3(0.f, 0.f, 0.f), g = f3(0.f, 0.f, 0.f), gs = f3(0.f, 0.f, 0.f), Qp = f3(0.f, 0.f, 0.f), Q0 = f3(0.f, 0.f, 0.f);
-    int rf_last = 0;  // ring face val-1 (tracked so that no local array is indexed dynamically)
-#pragma unroll
-    for (int i = 0; i < MAXV; i++) {
-      if (i >= val) break;
-      rf_last = rf[i];
-      const float4 Pn = sP[rn[i]];
-      const float3 E = sub3(Pn, Pv);
-      const float len2 = dot3(E, E);
-      const float rl = rsqrtf(len2);
-      const float dl = len2 * rl * inv_l0 - 1.0f;  // len/l0 - 1  (:156-160)
-      const int ip = (i == 0) ? val - 1 : i - 1;
-      // edge (v, n_i) belongs to ring faces i-1 and i; each contributes unit(E)*dl unless degenerate
-      const float w = (float)(2 - ((m >> (2 * i + 1)) & 1u) - ((m >> (2 * ip + 1)) & 1u));
-      const float sc = rl * dl * w;
-      T.x += E.x * sc; T.y += E.y * sc; T.z += E.z * sc;
-      const float3 Q = sub3(Pn, com);
-      if (i == 0) Q0 = Q;
-      else {
-        const float3 c = cross3(Qp, Q);  // gradient of ring face i-1 = (v, n_{i-1}, n_i)
-        g.x += c.x; g.y += c.y; g.z += c.z;
-        if (P.stale_from >= 0 && (int)rf[i - 1] >= P.stale_from) { gs.x += c.x; gs.y += c.y; gs.z += c.z; }
-      }
-      Qp = Q;
-    }
-    {
-      const float3 c = cross3(Qp, Q0);  // ring face val-1 = (v, n_{val-1}, n_0)
-      g.x += c.x; g.y += c.y; g.z += c.z;
-      if (P.stale_from >= 0 && rf_last >= P.stale_from) { gs.x += c.x; gs.y += c.y; gs.z += c.z; }
-    }
-    float3 F = f3(T.x * scale + coef * g.x + dcoef * gs.x, T.y * scale + coef * g.y + dcoef * gs.y, T.z * scale + coef * g.z + dcoef * gs.z);
+    float3 T = f3(0.f, 0.f, 0.f), g = f3(0.f, 0.f, 0.f), gs = f3(0.f, 0.f, 0.f);
+    if (__any_sync(__activemask(), (m & 0xaaaaaaaau) != 0u))
+      ring_gather<MAXV, MINV, true, COMPAT>(sP, rn, rf, val, m, Pv, com, inv_l0, P.stale_from, T, g, gs);
+    else
+      ring_gather<MAXV, MINV, false, COMPAT>(sP, rn, rf, val, m, Pv, com, inv_l0, P.stale_from, T, g, gs);
+    float3 F = f3(T.x * scale + coef * g.x, T.y * scale + coef * g.y, T.z * scale + coef * g.z);
+    if (COMPAT) { F.x += dcoef * gs.x; F.y += dcoef * gs.y; F.z += dcoef * gs.z; }
     if (doStick && ndown > 0) {
       const float nd = (float)ndown;  // one application per adjacent down-facing face (:226-246)
       const float h = fabsf(Pv.z);
       if (Pv.z < 0.0f) F.z += nd * (Ks * h);
       if (h < l0 * 2.0f) {
         const float3 ctv = f3(Pv.x - com.x, Pv.y - com.y, 0.0f - com.z);
-        const float ftmp = Ks * (1.0f - h / l0);
-        const float sc = rsqrtf(dot3(ctv, ctv)) * ftmp * nd;
+        const float ftmp = Ks * (1.0f - h * inv_l0);
+        const float sc = rsqrt_fast(dot3(ctv, ctv)) * ftmp * nd;
         F.x += ctv.x * sc; F.y += ctv.y * sc; F.z += ctv.z * sc;
       }
     }
@@ -723,21 +861,26 @@ __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DParams P
   __syncthreads();  // everyone is done reading start-of-step sP
 
   // ---- Euler update (EulerPosition :380), outputs ----------------------------------------------------------
+  VertPartial vp;
+  vp.init();
   for (int v = tid; v < nv; v += STEP_THREADS) {
     const float4 F = sF[v];
     float4 np = sP[v];
     np.x += F.x * P.dt; np.y += F.y * P.dt; np.z += F.z * P.dt;
     np.w = 0.f;
-    P.pos_out[(size_t)ci * nv + v] = np;
     if (P.force_out) P.force_out[(size_t)ci * nv + v] = F;
     sP[v] = np;
+    vp.add(np);
   }
+  fence_async_smem();  // this thread's sP writes -> visible to the bulk store issued below
   __syncthreads();
+  if (tid == 0) bulk_s2g(P.pos_out + (size_t)ci * nv, sP, (unsigned)(sizeof(float4) * nv));
 
   // ---- next step's per-cell scalars from the NEW positions --------------------------------------------------
   CellTopo T;
   T.faces = P.faces; T.ring_nbr = P.ring_nbr; T.valence = P.valence; T.ring_stride = P.ring_stride; T.nv = nv; T.nf = nf;
-  cell_scalars(sP, sTerm, T, bi2.w, P.bnd_out + BND * (size_t)ci, P.flag_out + (size_t)ci * nf, P.bbox_lo + ci, P.bbox_hi + ci, P.st);
+  cell_scalars(sP, sTerm, T, vp, bi2.w, P.bnd_out + BND * (size_t)ci, P.flag_out + (size_t)ci * nf, P.bbox_lo + ci, P.bbox_hi + ci, P.st);
+  if (tid == 0) bulk_wait_all();  // the bulk store has read sP (and landed) before the CTA's shared memory is released
 }
 
 }  // namespace dpm
