@@ -43,6 +43,8 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
+        global LIB_PATH
+        LIB_PATH = os.environ.get("DPM_B200_LIB", LIB_PATH)  # development: an alternative build of the same library
         if not os.path.exists(LIB_PATH):
             raise ImportError(f"{LIB_PATH} is missing: build it with `python -m opencl_dpm_b200.build` "
                               "(there is no CPU fallback)")

@@ -107,7 +107,10 @@ int pick_config(dpm3d_ctx *h) {
   return DPM_OK;
 }
 
-size_t smem_for(dpm3d_ctx *h) { return step3d_smem_bytes(h->nv, h->nf); }
+size_t smem_for(dpm3d_ctx *h) {
+  const char *pad = getenv("DPM_SMEM_PAD");  // experiments: extra dynamic shared memory per CTA (lowers the CTAs per SM)
+  return step3d_smem_bytes(h->nv, h->nf) + (pad ? (size_t)atoi(pad) : 0);
+}
 
 // The step kernel variant for this mesh: ring slots read per vertex / slots every vertex has, and the compat mode.
 template <typename Fn>
@@ -413,23 +416,42 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
     DPM_CUDA_TRY(cudaMemcpyAsync(&h->st->rebuild, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     h->last_pbc = pbc; h->last_L = L;
   }
+  // DPM_TRACE: device time of each kernel of ONE timestep in the middle of the call (events on the stream)
+  static const bool trace = getenv("DPM_TRACE") != nullptr;
+  const int traced = (trace && nsteps >= 4) ? nsteps / 2 : -1;
+  cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int s = 0; s < nsteps; s++) {
+    const bool tr = s == traced;
+    if (tr) for (auto &e : tev) cudaEventCreate(&e);
     if (h->nranks > 1) {  // ghosts of the current state + the global rebuild decision (dpm_halo.cu)
       int rc = shard_exchange(h, pbc, L);
       if (rc) return rc;
     }
+    if (tr) cudaEventRecord(tev[0], h->stream);
     DPM_CUDA_TRY(launch_rebuild(nbr_buffers(h, pbc, L), h->stream, h->coop_grid));
+    if (tr) cudaEventRecord(tev[1], h->stream);
     p.pos_in = h->pos[h->cur]; p.pos_out = h->pos[h->cur ^ 1];
     p.bnd_in = h->bnd[h->cur]; p.bnd_out = h->bnd[h->cur ^ 1];
     p.flag_in = h->flag[h->cur]; p.flag_out = h->flag[h->cur ^ 1];
     p.force_out = (s == nsteps - 1) ? h->force : nullptr;  // forces are only read back after the last step (:425-434)
     if (repel) {
       dpm3d_units_kernel<<<h->nc, UNITS_THREADS, 0, h->stream>>>(p);
+      if (tr) cudaEventRecord(tev[2], h->stream);
       dpm3d_contact_kernel<<<h->contact_grid, CONTACT_THREADS, 0, h->stream>>>(p);
       DPM_CUDA_TRY(cudaGetLastError());
-    }
+    } else if (tr) cudaEventRecord(tev[2], h->stream);
+    if (tr) cudaEventRecord(tev[3], h->stream);
     DPM_CUDA_TRY(launch_step(h, p));
+    if (tr) cudaEventRecord(tev[4], h->stream);
     h->cur ^= 1;
+  }
+  if (traced >= 0) {
+    cudaEventSynchronize(tev[4]);
+    float t[4];
+    for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
+    fprintf(stderr, "[dpm3d] timestep %d of %d (us): rebuild %.1f  units %.1f  contact %.1f  step %.1f  total %.1f\n", traced, nsteps,
+            t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f, (t[0] + t[1] + t[2] + t[3]) * 1e3f);
+    for (auto &e : tev) cudaEventDestroy(e);
   }
   h->stats.steps += (uint64_t)nsteps;
   h->stats.launches += (repel ? 4ull : 2ull) * (uint64_t)nsteps;

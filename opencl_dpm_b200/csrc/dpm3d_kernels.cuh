@@ -91,8 +91,11 @@ __device__ __forceinline__ float group_sum(float v, unsigned gmask) {
   return v;
 }
 
+// sP[nv] | sF[max(nv, ceil(nf/2))] (forces; the epilogue reuses it for the signed-volume terms, two per float4 so that the
+// serial chains read them with the vertex stride) | sFlag[nf]
+__host__ __device__ inline int step3d_mid_slots(int nv, int nf) { return nv > (nf + 1) / 2 ? nv : (nf + 1) / 2; }
 inline size_t step3d_smem_bytes(int nv, int nf) {
-  return sizeof(float4) * 2 * (size_t)nv + sizeof(float) * nf + ((nf + 15) / 16) * 16 + 64;  // sP, sF, sTerm, sFlag
+  return sizeof(float4) * ((size_t)nv + step3d_mid_slots(nv, nf)) + ((nf + 15) / 16) * 16 + 64;
 }
 
 __device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
@@ -122,8 +125,17 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
   return r;
 }
 
-// ---- 1-D bulk copies through the async proxy (TMA unit): one instruction moves a whole cell -------------------
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// 8-byte shared-memory load at a 32-bit shared address + immediate offset (one LDS.64, no generic addressing)
+template <int OFF>
+__device__ __forceinline__ float2 lds_v2(unsigned addr) {
+  float2 t;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(t.x), "=f"(t.y) : "r"(addr), "n"(OFF));
+  return t;
+}
+
+// ---- 1-D bulk copies through the async proxy (TMA unit): one instruction moves a whole cell -------------------
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -491,7 +503,7 @@ __device__ __forceinline__ bool face_sees_centre(float4 P0, float3 n, float nn, 
 // volume (the four chains run in four lanes of ONE warp, rotated over the CTA's warps by the cell index so that every
 // SM sub-partition gets its share of them), r^2 max/min about the COM, longest edge (-> contact pad) and the
 // star-shape flag.  Used by the bounds kernel (after an upload) and by the step kernel's epilogue (for the NEW
-// positions).  Block of STEP_THREADS threads; sTerm: nf floats of scratch.  Every thread passes the partial vertex
+// positions).  Block of STEP_THREADS threads; sWide: max(nv, ceil(nf/2)) float4 of scratch.  Every thread passes the partial vertex
 // sum and partial AABB of the vertices it staged / integrated (tid, tid + STEP_THREADS, ...).
 //   bnd[0] = (lo.xyz, r2max)   bnd[1] = (hi.xyz, pad)   bnd[2] = (com.xyz, volume)   bnd[3] = (r2min, star, vol_prev, 0)
 // ---------------------------------------------------------------------------------
@@ -520,7 +532,7 @@ struct VertPartial {  // per-thread partials over the thread's own vertices
   }
 };
 
-__device__ __forceinline__ void cell_scalars(const float4 *sP, float *sTerm, const CellTopo &T, VertPartial vp, float vol_prev,
+__device__ __forceinline__ void cell_scalars(const float4 *sP, float4 *sWide, const CellTopo &T, VertPartial vp, float vol_prev,
                                              float4 *bnd_cell, unsigned char *flag_cell, const float4 *bbox_lo, const float4 *bbox_hi,
                                              NbrState *st) {
   __shared__ float sRed[STEP_WARPS][12];
@@ -550,6 +562,7 @@ __device__ __forceinline__ void cell_scalars(const float4 *sP, float *sTerm, con
   // ONE pass over the faces: signed-volume term dot(cross(P0,P1),P2)/6.0f in the reference's operation order, unfused
   // (shaders/Cell3D_Kernel.cl:58-61); star-shape test; next step's facing-the-substrate (StickToSurface :209-214) and
   // degenerate-edge (:151) flags
+  float *sTerm = reinterpret_cast<float *>(sWide);  // term f at float 4*(f/2) + (f&1): pair k = (2k, 2k+1) in sWide[k].xy
   int star = 1;
   float e2 = 0.0f;
   for (int f = tid; f < nf; f += STEP_THREADS) {
@@ -558,7 +571,7 @@ __device__ __forceinline__ void cell_scalars(const float4 *sP, float *sTerm, con
     const float cx = __fsub_rn(__fmul_rn(P0.y, P1.z), __fmul_rn(P0.z, P1.y));
     const float cy = __fsub_rn(__fmul_rn(P0.z, P1.x), __fmul_rn(P0.x, P1.z));
     const float cz = __fsub_rn(__fmul_rn(P0.x, P1.y), __fmul_rn(P0.y, P1.x));
-    sTerm[f] = div6_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, P2.x), __fmul_rn(cy, P2.y)), __fmul_rn(cz, P2.z)));
+    sTerm[4 * (f >> 1) + (f & 1)] = div6_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, P2.x), __fmul_rn(cy, P2.y)), __fmul_rn(cz, P2.z)));
     const float3 A = sub3(P1, P0), B = sub3(P2, P0), C = sub3(P2, P1);
     const float3 n = cross3(A, B);
     const float nn = dot3(n, n);
@@ -573,31 +586,31 @@ __device__ __forceinline__ void cell_scalars(const float4 *sP, float *sTerm, con
   if (lane == 0) sRed[warp][9] = e2;
   __syncthreads();
   // The serial chains (:35-44 COM, :46-64 volume): lane 0/1/2 = COM x/y/z, lane 3 = signed volume.  Every iteration
-  // is one 8-byte LDS (lanes 0,1: sP[k].xy; lane 2: sP[k].zw; lane 3: terms 2k, 2k+1) and two predicated FADDs.
+  // is one 8-byte LDS with the same 16-byte stride in all four lanes (lanes 0,1: sP[k].xy; lane 2: sP[k].zw; lane 3:
+  // sWide[k].xy = terms 2k, 2k+1) and two predicated FADDs.
   if (warp == (int)(blockIdx.x & (STEP_WARPS - 1)) && lane < 4) {
-    const float2 *src = (lane == 3) ? reinterpret_cast<const float2 *>(sTerm) : reinterpret_cast<const float2 *>(sP) + (lane == 2 ? 1 : 0);
-    const int stride = (lane == 3) ? 1 : 2;  // in float2
+    unsigned addr = (lane == 3) ? smem_addr(sWide) : smem_addr(sP) + (lane == 2 ? 8u : 0u);
     const bool useA = lane != 1, useB = (lane & 1) != 0;
     const int cnt = (lane == 3) ? (nf >> 1) : nv;
     const int ncommon = min(nv, nf >> 1);
     float s = 0.0f;
     int k = 0;
-    for (; k + 8 <= ncommon; k += 8) {
+    for (; k + 8 <= ncommon; k += 8, addr += 128u) {
       float2 t[8];
-#pragma unroll
-      for (int q = 0; q < 8; q++) t[q] = src[(k + q) * stride];
+      t[0] = lds_v2<0>(addr); t[1] = lds_v2<16>(addr); t[2] = lds_v2<32>(addr); t[3] = lds_v2<48>(addr);
+      t[4] = lds_v2<64>(addr); t[5] = lds_v2<80>(addr); t[6] = lds_v2<96>(addr); t[7] = lds_v2<112>(addr);
 #pragma unroll
       for (int q = 0; q < 8; q++) {
         if (useA) s = __fadd_rn(s, t[q].x);
         if (useB) s = __fadd_rn(s, t[q].y);
       }
     }
-    for (; k < cnt; k++) {
-      const float2 t = src[k * stride];
+    for (; k < cnt; k++, addr += 16u) {
+      const float2 t = lds_v2<0>(addr);
       if (useA) s = __fadd_rn(s, t.x);
       if (useB) s = __fadd_rn(s, t.y);
     }
-    if (lane == 3 && (nf & 1)) s = __fadd_rn(s, sTerm[nf - 1]);
+    if (lane == 3 && (nf & 1)) s = __fadd_rn(s, sTerm[4 * (nf >> 1)]);
     sSc[lane] = (lane == 3) ? fabsf(s) : __fmul_rn(s, __fdiv_rn(1.0f, (float)nv));
   }
   __syncthreads();
@@ -632,7 +645,7 @@ static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_bounds_kernel(const
                                                                            CellTopo T) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 *sP = reinterpret_cast<float4 *>(smem_raw);
-  float *sTerm = reinterpret_cast<float *>(sP + 2 * T.nv);  // same carve-up as the step kernel (sP, sF, sTerm, sFlag)
+  float4 *sWide = sP + T.nv;  // same carve-up as the step kernel (sP | sF | sFlag)
   const int ci = blockIdx.x;
   VertPartial vp;
   vp.init();
@@ -642,7 +655,7 @@ static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_bounds_kernel(const
     vp.add(p);
   }
   __syncthreads();
-  cell_scalars(sP, sTerm, T, vp, 0.0f, bnd + BND * (size_t)ci, flags + (size_t)ci * T.nf, nullptr, nullptr, nullptr);
+  cell_scalars(sP, sWide, T, vp, 0.0f, bnd + BND * (size_t)ci, flags + (size_t)ci * T.nf, nullptr, nullptr, nullptr);
 }
 
 // Walk-start table of the fast contact evaluation: for the direction of each octahedral texel, the face of cell 0 whose
@@ -756,8 +769,7 @@ __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DParams P
   const int nv = P.nv, nf = P.nf;
   float4 *sP = reinterpret_cast<float4 *>(smem_raw);
   float4 *sF = sP + nv;
-  float *sTerm = reinterpret_cast<float *>(sF + nv);
-  unsigned char *sFlag = reinterpret_cast<unsigned char *>(sTerm + nf);
+  unsigned char *sFlag = reinterpret_cast<unsigned char *>(sF + step3d_mid_slots(nv, nf));
   const int tid = threadIdx.x;
   const int ci = blockIdx.x;
   const float4 *gP = P.pos_in + (size_t)ci * nv;
@@ -879,7 +891,7 @@ __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DParams P
   // ---- next step's per-cell scalars from the NEW positions --------------------------------------------------
   CellTopo T;
   T.faces = P.faces; T.ring_nbr = P.ring_nbr; T.valence = P.valence; T.ring_stride = P.ring_stride; T.nv = nv; T.nf = nf;
-  cell_scalars(sP, sTerm, T, vp, bi2.w, P.bnd_out + BND * (size_t)ci, P.flag_out + (size_t)ci * nf, P.bbox_lo + ci, P.bbox_hi + ci, P.st);
+  cell_scalars(sP, sF, T, vp, bi2.w, P.bnd_out + BND * (size_t)ci, P.flag_out + (size_t)ci * nf, P.bbox_lo + ci, P.bbox_hi + ci, P.st);
   if (tid == 0) bulk_wait_all();  // the bulk store has read sP (and landed) before the CTA's shared memory is released
 }
 
