@@ -66,6 +66,17 @@ struct Step3DParams {
   int stale_from;  // >= 0: reference-race compatibility mode (dpm3d_set_compat), else -1
 };
 
+#define DPM_PRAGMA_(x) _Pragma(#x)
+#define DPM_UNROLL(n) DPM_PRAGMA_(unroll n)
+#ifndef DPM_FACE_UNROLL
+#define DPM_FACE_UNROLL 2  // unroll factors of the step kernel's face and vertex loops (sweep in profiles/)
+#endif
+#ifndef DPM_RING_UNROLL
+#define DPM_RING_UNROLL 1
+#endif
+#ifndef DPM_STEP_MINB
+#define DPM_STEP_MINB 1  // CTAs per SM promised to ptxas for the step kernel (1 = no register cap); see profiles/ for the sweep
+#endif
 constexpr int UNIT_CAP_FACTOR = 2;  // unit list capacity = factor * THREADS
 constexpr int BND = 4;              // float4 per cell in the bounds arrays:
                                     //   (lo.xyz, r2max) (hi.xyz, contact pad) (com.xyz, volume) (r2min, star flag, 0, 0)
@@ -565,6 +576,7 @@ __device__ __forceinline__ void cell_scalars(const float4 *sP, float4 *sWide, co
   float *sTerm = reinterpret_cast<float *>(sWide);  // term f at float 4*(f/2) + (f&1): pair k = (2k, 2k+1) in sWide[k].xy
   int star = 1;
   float e2 = 0.0f;
+  DPM_UNROLL(DPM_FACE_UNROLL)
   for (int f = tid; f < nf; f += STEP_THREADS) {
     const ushort4 fc = __ldg(T.faces + f);
     const float4 P0 = sP[fc.x], P1 = sP[fc.y], P2 = sP[fc.z];
@@ -763,7 +775,7 @@ __device__ __forceinline__ void ring_gather(const float4 *sP, const unsigned sho
 // MAXV: ring slots read per vertex (6: valence 5..6, the icospheres; 8; 16 = two 16-byte loads); MINV: ring slots
 // known to be occupied for every vertex (no bound check)
 template <int MAXV, int MINV, bool COMPAT>
-__global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DParams P) {
+__global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel(Step3DParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long sBar;
   const int nv = P.nv, nf = P.nf;
@@ -806,6 +818,7 @@ __global__ void __launch_bounds__(STEP_THREADS) dpm3d_step_kernel(Step3DParams P
   mbar_wait(&sBar, 0);
 
   // ---- ring pass: every vertex gathers over its constant ring adjacency ---------------------------------
+  DPM_UNROLL(DPM_RING_UNROLL)
   for (int v = tid; v < nv; v += STEP_THREADS) {
     const int val = (MINV == MAXV) ? MAXV : (int)__ldg(P.valence + v);
     // ring tables: 8 x uint16 per vertex = one 16-byte load each (valence <= 8; the stride-16 layout takes two)
