@@ -133,11 +133,21 @@ cudaError_t set_smem(dpm3d_ctx *h) {
   return cudaFuncSetAttribute(dpm3d_bounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
+// Launch with programmatic stream serialization: the kernel's CTAs may be scheduled while the kernel ahead of it in the
+// stream drains, and run up to their griddep_wait() (dpm3d_kernels.cuh).
+template <typename K>
+static cudaError_t launch_pdl(K *kernel, int grid, int block, size_t smem, cudaStream_t stream, const Step3DParams &p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 cudaError_t launch_step(dpm3d_ctx *h, const Step3DParams &p) {
-  return with_step_kernel(h, [&](auto *k) {
-    k<<<p.nc, STEP_THREADS, h->smem, h->stream>>>(p);
-    return cudaGetLastError();
-  });
+  return with_step_kernel(h, [&](auto *k) { return launch_pdl(k, p.nc, STEP_THREADS, h->smem, h->stream, p); });
 }
 
 CellTopo cell_topo(dpm3d_ctx *h) {
@@ -435,10 +445,9 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
     p.flag_in = h->flag[h->cur]; p.flag_out = h->flag[h->cur ^ 1];
     p.force_out = (s == nsteps - 1) ? h->force : nullptr;  // forces are only read back after the last step (:425-434)
     if (repel) {
-      dpm3d_units_kernel<<<h->nc, UNITS_THREADS, 0, h->stream>>>(p);
+      DPM_CUDA_TRY(launch_pdl(dpm3d_units_kernel, h->nc, UNITS_THREADS, 0, h->stream, p));
       if (tr) cudaEventRecord(tev[2], h->stream);
-      dpm3d_contact_kernel<<<h->contact_grid, CONTACT_THREADS, 0, h->stream>>>(p);
-      DPM_CUDA_TRY(cudaGetLastError());
+      DPM_CUDA_TRY(launch_pdl(dpm3d_contact_kernel, h->contact_grid, CONTACT_THREADS, 0, h->stream, p));
     } else if (tr) cudaEventRecord(tev[2], h->stream);
     if (tr) cudaEventRecord(tev[3], h->stream);
     DPM_CUDA_TRY(launch_step(h, p));

@@ -138,6 +138,13 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// Programmatic dependent launch (the timestep's kernels are chained with cudaLaunchAttributeProgrammaticStreamSerialization):
+// griddep_wait() blocks until the preceding kernel of the stream has completed and its writes are visible (a no-op when
+// the kernel was launched without the attribute); griddep_launch() lets the following kernel's CTAs be scheduled once
+// every CTA of this grid has called it or exited.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // 8-byte shared-memory load at a 32-bit shared address + immediate offset (one LDS.64, no generic addressing)
 template <int OFF>
 __device__ __forceinline__ float2 lds_v2(unsigned addr) {
@@ -359,7 +366,16 @@ static __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3
   __shared__ int sBase;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ci = blockIdx.x, nv = P.nv, K = P.K;
+  griddep_launch();
+  // state of the previous timestep's step kernel (complete before the kernel ahead of this one started): read it now
   const float4 bi0 = P.bnd_in[BND * (size_t)ci], bi1 = P.bnd_in[BND * (size_t)ci + 1], bi2 = P.bnd_in[BND * (size_t)ci + 2];
+  float4 myp[UNITS_VPT];
+#pragma unroll
+  for (int j = 0; j < UNITS_VPT; j++) {
+    const int v = tid + j * UNITS_THREADS;
+    myp[j] = (v < nv) ? P.pos_in[(size_t)ci * nv + v] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  griddep_wait();  // the candidate lists (and the unit counter) belong to the rebuild kernel ahead
   const int ncand = min(P.cand_count[ci], K);
   int nact = 0;
   for (int k = tid; k < ncand; k += UNITS_THREADS) {
@@ -387,7 +403,6 @@ static __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3
     if (tid == 0) { P.unit_base[ci] = 0; P.unit_cnt[ci] = 0; }
     return;
   }
-  float4 myp[UNITS_VPT];
   int cntj[UNITS_VPT];
   int cnt = 0;
 #pragma unroll
@@ -395,8 +410,7 @@ static __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3
     const int v = tid + j * UNITS_THREADS;
     cntj[j] = 0;
     if (v < nv) {
-      const float4 p = P.pos_in[(size_t)ci * nv + v];
-      myp[j] = p;
+      const float4 p = myp[j];
       for (int k = 0; k < ncand; k++) {
         if (sCand[k] < 0) continue;
         const float4 lo = sLo[k], hi = sHi[k], sp = sSph[k];
@@ -468,6 +482,8 @@ static __global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(S
   const int gshift = lane & ~(UNIT_LANES - 1);
   const unsigned gmask = ((1u << UNIT_LANES) - 1u) << gshift;
   const int ngroups = gridDim.x * (CONTACT_THREADS / UNIT_LANES);
+  griddep_launch();  // the step kernel may start its shape-force pass next to this kernel
+  griddep_wait();    // the unit list of the units kernel
   const int total = min(P.st->unit_total, P.unit_cap);
   const int nv = P.nv;
   // warp-uniform trip count: the 4 groups of a warp take 4 consecutive units and stay in lockstep
@@ -812,8 +828,6 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
   const float inv_l0 = 1.0f / l0;
   const float scale = doArea ? Ka * sqrtf(a0) / l0 * 0.3f : 0.0f;  // :162
   const bool doRep = (P.mask & DPM3D_REPEL) && P.Kc != 0.0f;
-  const int ucnt = doRep ? P.unit_cnt[ci] : 0;
-  const float *uw = P.unit_w + (doRep ? P.unit_base[ci] : 0);
   __syncthreads();  // the barrier is initialised (and the plain flag copy, if any, is complete)
   mbar_wait(&sBar, 0);
 
@@ -861,6 +875,20 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
         F.x += ctv.x * sc; F.y += ctv.y * sc; F.z += ctv.z * sc;
       }
     }
+    sF[v] = make_float4(F.x, F.y, F.z, 0.f);
+  }
+  __syncthreads();  // everyone is done reading start-of-step sP
+
+  // ---- Euler update (EulerPosition :380), outputs ----------------------------------------------------------
+  // The contact weights are the only input from this timestep's units / contact kernels: everything above overlaps them.
+  griddep_wait();
+  const int ucnt = doRep ? P.unit_cnt[ci] : 0;
+  const float *uw = P.unit_w + (doRep ? P.unit_base[ci] : 0);
+  VertPartial vp;
+  vp.init();
+  for (int v = tid; v < nv; v += STEP_THREADS) {
+    float4 F = sF[v];
+    float4 np = sP[v];
     // fold this vertex's evaluated contact units (ordered by ascending neighbour id: the reference's cj order)
     if (ucnt > 0) {
       const unsigned ui = P.unit_idx[(size_t)ci * nv + v];
@@ -871,7 +899,7 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
         const float wn = uw[u];
         if (!(fabsf(wn) < 1e-6f)) {  // :302-308
           if (!have) {
-            const float3 d = f3(com.x - Pv.x, com.y - Pv.y, com.z - Pv.z);
+            const float3 d = f3(com.x - np.x, com.y - np.y, com.z - np.z);
             const float r = rsqrtf(dot3(d, d));
             dir = f3(d.x * r, d.y * r, d.z * r);
             have = true;
@@ -881,16 +909,6 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
         }
       }
     }
-    sF[v] = make_float4(F.x, F.y, F.z, 0.f);
-  }
-  __syncthreads();  // everyone is done reading start-of-step sP
-
-  // ---- Euler update (EulerPosition :380), outputs ----------------------------------------------------------
-  VertPartial vp;
-  vp.init();
-  for (int v = tid; v < nv; v += STEP_THREADS) {
-    const float4 F = sF[v];
-    float4 np = sP[v];
     np.x += F.x * P.dt; np.y += F.y * P.dt; np.z += F.z * P.dt;
     np.w = 0.f;
     if (P.force_out) P.force_out[(size_t)ci * nv + v] = F;
