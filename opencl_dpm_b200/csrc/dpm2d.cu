@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <chrono>
 #include <vector>
 
 #include "dpm_common.cuh"
@@ -211,8 +212,10 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
               const float dist = sqrtf(rx * rx + ry * ry);
               if (dist < l0) {
                 const float ftmp = P.Kat / (float)n * dist / l0;  // :263
-                tx = ftmp * (rx / dist);
-                ty = ftmp * (ry / dist);
+                if (dist != 0.0f) {  // OpenCL normalize(0) = 0 (two coinciding vertices; measured on the reference's runtime)
+                  tx = ftmp * (rx / dist);
+                  ty = ftmp * (ry / dist);
+                }
                 hit = true;
               }
             }
@@ -261,8 +264,10 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
       const float dist = sqrtf(dx * dx + dy * dy);
       const float xij = dist / (2.0f * r0);
       const float ftmp = P.Kre * (1.0f - xij);
-      f.x += 0.5f * ftmp * (dx / dist);
-      f.y += 0.5f * ftmp * (dy / dist);
+      if (dist != 0.0f) {  // normalize(0) = 0
+        f.x += 0.5f * ftmp * (dx / dist);
+        f.y += 0.5f * ftmp * (dy / dist);
+      }
     }
     const float2 np = make_float2(p.x + f.x * P.dt, p.y + f.y * P.dt);
     P.pos_out[(size_t)ci * S + vi] = np;
@@ -314,6 +319,7 @@ struct dpm2d_ctx {
   int *bin_id = nullptr, *order = nullptr, *bin_count = nullptr, *bin_start = nullptr, *cand_count = nullptr, *cand = nullptr;
   float *partial = nullptr;
   int *chunk_sum = nullptr;
+  int *ext_list = nullptr;
   int cap = 0, K = 32, K_alloc = 0;
   float skin_rel = 0.1f;
   int coop_grid = 0;
@@ -346,7 +352,7 @@ NbrBuffers nbr_buffers2(dpm2d_ctx *h, float range, int pbc, float L) {
   nb.bin_id = h->bin_id; nb.order = h->order; nb.bin_count = h->bin_count; nb.bin_start = h->bin_start;
   nb.cand_count = h->cand_count; nb.cand = h->cand; nb.partial = h->partial; nb.chunk_sum = h->chunk_sum;
   nb.nc = h->nc; nb.nc_list = h->nc; nb.nd = 2; nb.cap = h->cap; nb.K = h->K;
-  nb.pbc = pbc; nb.L = L; nb.skin_rel = h->skin_rel; nb.range = range; nb.far2d = 1;
+  nb.pbc = pbc; nb.L = L; nb.skin_rel = h->skin_rel; nb.range = range; nb.far2d = 1; nb.ext_list = h->ext_list;
   return nb;
 }
 
@@ -425,6 +431,7 @@ int dpm2d_create(dpm2d_t **out, int device, int ncells, int max_nv) {
   h->coop_grid = rebuild_max_grid(device);
   TRYB(cudaMalloc(&h->partial, sizeof(float) * 16 * h->coop_grid));
   TRYB(cudaMalloc(&h->chunk_sum, sizeof(int) * h->coop_grid));
+  TRYB(cudaMalloc(&h->ext_list, sizeof(int) * h->nc));
   int rc = alloc_cand2(h);
   if (rc) return bail(rc);
   TRYB(cudaFuncSetAttribute(dpm2d_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2d_bytes(max_nv)));
@@ -438,7 +445,7 @@ int dpm2d_destroy(dpm2d_t *h) {
   DeviceGuard2 guard(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   void *ptrs[] = {h->pos[0], h->pos[1], h->force, h->bnd[0], h->bnd[1], h->nv, h->cellA, h->cellB, h->st, h->bbox_lo, h->bbox_hi,
-                  h->bin_id, h->order, h->bin_count, h->bin_start, h->cand_count, h->cand, h->partial, h->chunk_sum};
+                  h->bin_id, h->order, h->bin_count, h->bin_start, h->cand_count, h->cand, h->partial, h->chunk_sum, h->ext_list};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (h->h_cell) cudaFreeHost(h->h_cell);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -566,14 +573,28 @@ int dpm2d_euler_update(dpm2d_t *h, float *verts2, float *forces2, const int32_t 
   if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
   if (nsteps <= 0) return fail(DPM_ERR_INVALID_ARGUMENT, "nsteps must be positive");
   DeviceGuard2 guard(h->device);
+  static const bool trace = getenv("DPM_TRACE") != nullptr;  // host-side phase times of the call on stderr
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  auto ms_since = [&](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
+  double t_up = 0, t_enq = 0, t_run = 0;
   for (int attempt = 0;; attempt++) {
     int rc = dpm2d_upload(h, verts2, nv, Ka, Kl, Kb, a0, l0, r0);
     if (rc) return rc;
+    t_up = ms_since(t0);
     DPM_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     rc = dpm2d_step(h, nsteps, dt, Kre, Kat, pbc, L);
     if (rc) return rc;
     DPM_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    t_enq = ms_since(t0);
     rc = check_flags2(h);
+    t_run = ms_since(t0);
+    if (trace) {
+      float dev_ms = 0.f;
+      cudaEventElapsedTime(&dev_ms, h->ev0, h->ev1);
+      fprintf(stderr, "[dpm2d] euler_update %d steps attempt %d (K=%d): upload %.3f ms, steps enqueued %.3f, steps done %.3f (device loop %.3f) rc=%d\n",
+              nsteps, attempt, h->K, t_up, t_enq, t_run, dev_ms, rc);
+    }
     if (rc == DPM_ERR_RUNTIME && h->K < 128 && attempt < 3) {
       int rc2 = dpm2d_set_neighbor_params(h, h->skin_rel, std::min(128, h->K * 2));
       if (rc2) return rc2;

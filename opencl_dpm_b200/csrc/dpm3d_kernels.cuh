@@ -201,9 +201,10 @@ __host__ __device__ inline int octa_texel(float x, float y, float z) {
 __device__ __forceinline__ void solid_angle_terms(float3 a, float3 b, float3 c, float &den, float &num) {
   float da = dot3(a, a), db = dot3(b, b), dc = dot3(c, c);
   float ra = rsqrtf(da), rb = rsqrtf(db), rc = rsqrtf(dc);
-  ra = ra * (1.5f - 0.5f * da * ra * ra);
-  rb = rb * (1.5f - 0.5f * db * rb * rb);
-  rc = rc * (1.5f - 0.5f * dc * rc * rc);
+  // OpenCL normalize(0) = 0 (the vertex coincides with a corner; measured on the reference's runtime, see oracle/)
+  ra = da > 0.0f ? ra * (1.5f - 0.5f * da * ra * ra) : 0.0f;
+  rb = db > 0.0f ? rb * (1.5f - 0.5f * db * rb * rb) : 0.0f;
+  rc = dc > 0.0f ? rc * (1.5f - 0.5f * dc * rc * rc) : 0.0f;
   a = f3(a.x * ra, a.y * ra, a.z * ra); b = f3(b.x * rb, b.y * rb, b.z * rb); c = f3(c.x * rc, c.y * rc, c.z * rc);
   den = 1.0f + dot3(a, b) + dot3(b, c) + dot3(c, a);
   num = dot3(a, cross3(b, c));
@@ -247,7 +248,7 @@ static __device__ __noinline__ float omega_skipped_f64(float3 a, float3 b, float
 }
 
 // Returns 0 on success, else the reason the caller must fall back to the literal sum (1: vertex within the pad of
-// the neighbour's COM, 2: walk limit, 3: ring limit).
+// the neighbour's COM or exactly on one of its vertices, 2: walk limit, 3: ring limit).
 // Warp-uniform version: the warp's 4 groups (UNIT_LANES = 8 lanes each) hold 4 different units and advance in
 // lockstep (every loop runs while ANY group needs it, idle groups are predicated off), so the heavy per-face math is
 // issued once for all four.  `active` = this lane's group has a unit.  Returns 0 on success, else the reason the
@@ -302,7 +303,7 @@ __device__ __forceinline__ int winding_fast(const Step3DParams &P, bool active, 
   for (int base = 0; base < RING_TAB; base += UNIT_LANES) {
     if (!__any_sync(FULL, open)) break;
     const int j = base + g;
-    bool hit = false;
+    bool hit = false, coincident = false;
     const int jlast = (int)((rends >> (8 * RING_MAX)) & 0xff);
     if (open && j < jlast) {
       const int gf = __ldg(tab + j);
@@ -329,10 +330,13 @@ __device__ __forceinline__ int winding_fast(const Step3DParams &P, bool active, 
         float den, num;
         solid_angle_terms(a, b, c, den, num);
         if (den < 1e-8f) corr += omega_skipped_f64(a, b, c);
+        // p ON a corner: the reference's normalize(0) = 0 zeroes that face's term, which W - sum(skipped) cannot express
+        coincident = dot3(a, a) == 0.0f || dot3(b, b) == 0.0f || dot3(c, c) == 0.0f;
       }
     }
     const unsigned bal = __ballot_sync(FULL, hit);
     hits |= (unsigned long long)((bal >> gshift) & 0xffu) << base;
+    if ((__ballot_sync(FULL, coincident) >> gshift) & 0xffu) { why = 1; open = false; }
     // every ring that is now completely examined must have touched the cone, else the patch is closed
     while (open && ring <= RING_MAX) {
       const int rb = (int)((rends >> (8 * (ring - 1))) & 0xff), re2 = (int)((rends >> (8 * ring)) & 0xff);

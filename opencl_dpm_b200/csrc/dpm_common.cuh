@@ -26,7 +26,7 @@ struct NbrState {
   int rebuild;   // lists are stale: rebuild before the next step
   int overflow;  // a candidate list exceeded K
   int nbuilds;
-  int pad;
+  int next;  // 2D: cells near the global extremes (the only possible |d| > L wrap partners), length of NbrBuffers::ext_list
   unsigned long long contact_evals;
   unsigned long long literal_evals;  // 3D: units that needed the literal all-faces sum (fallback of the fast path)
   unsigned long long fallback_why[4];
@@ -70,6 +70,7 @@ struct NbrBuffers {
   int range_from_bounds;  // 1: range = range_scale * max_c bhi[c].w (per-cell contact pad), recorded in st->range
   float range_scale;
   int far2d;
+  int *ext_list;  // far2d: [nc] scratch, the cells near the global extremes (filled by the rebuild kernel)
 };
 
 // Launches the cooperative rebuild kernel (no-op on the device when st->rebuild == 0).

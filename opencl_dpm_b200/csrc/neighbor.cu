@@ -171,7 +171,10 @@ __global__ void __launch_bounds__(RB_THREADS) nbr_rebuild_kernel(NbrBuffers nb) 
 
   // ---- P2: zero the histogram ----
   for (int b = gtid; b <= g.nbins; b += nthreads) nb.bin_count[b] = 0;
+  if (gtid == 0) nb.st->next = 0;
   grid.sync();
+  const float Lm = __fsub_rn(nb.L, skin);
+  const bool far2d = nb.far2d && nb.nd == 2 && nb.pbc && nb.ext_list;
 
   // ---- P3: bin ids + histogram ----
   for (int c = gtid; c < nb.nc; c += nthreads) {
@@ -179,6 +182,13 @@ __global__ void __launch_bounds__(RB_THREADS) nbr_rebuild_kernel(NbrBuffers nb) 
     const int id = (ib.z * g.nb[1] + ib.y) * g.nb[0] + ib.x;
     nb.bin_id[c] = id;
     atomicAdd(&nb.bin_count[id], 1);
+    if (far2d) {
+      // cells that can see (or be) a |d| > L wrap partner: only those near the global extremes
+      const float4 lo = nb.blo[(size_t)c * nb.blo_stride], hi = nb.bhi[(size_t)c * nb.blo_stride];
+      const bool maybe = (__fsub_rn(nb.st->ghi[0], lo.x) > Lm) || (__fsub_rn(hi.x, nb.st->glo[0]) > Lm) ||
+                         (__fsub_rn(nb.st->ghi[1], lo.y) > Lm) || (__fsub_rn(hi.y, nb.st->glo[1]) > Lm);
+      if (maybe) nb.ext_list[atomicAdd(&nb.st->next, 1)] = c;
+    }
   }
   grid.sync();
 
@@ -245,7 +255,6 @@ __global__ void __launch_bounds__(RB_THREADS) nbr_rebuild_kernel(NbrBuffers nb) 
   grid.sync();
 
   // ---- P7: candidate lists (thread per cell) + build-time boxes ----
-  const float Lm = __fsub_rn(nb.L, skin);
   const float hskin = 0.5f * skin;
   for (int i = gtid; i < nb.nc; i += nthreads) {
     const float4 loi = nb.blo[(size_t)i * nb.blo_stride], hii = nb.bhi[(size_t)i * nb.blo_stride];
@@ -279,12 +288,15 @@ __global__ void __launch_bounds__(RB_THREADS) nbr_rebuild_kernel(NbrBuffers nb) 
         }
       }
     }
-    if (nb.far2d && nb.nd == 2 && nb.pbc) {
-      // cells that can see a |d| > L wrap partner: only those near the global extremes
+    if (far2d) {
+      // a wrap partner j of i has farx or fary below, which puts BOTH cells near opposite global extremes: only the
+      // extreme cells look, and only at the extreme cells (their order in ext_list does not matter: tmp is sorted)
       const bool maybe = (__fsub_rn(nb.st->ghi[0], loi.x) > Lm) || (__fsub_rn(hii.x, nb.st->glo[0]) > Lm) ||
                          (__fsub_rn(nb.st->ghi[1], loi.y) > Lm) || (__fsub_rn(hii.y, nb.st->glo[1]) > Lm);
       if (maybe) {
-        for (int j = 0; j < nb.nc; j++) {
+        const int next = nb.st->next;
+        for (int e = 0; e < next; e++) {
+          const int j = nb.ext_list[e];
           if (j == i) continue;
           const float4 loj = nb.blo[(size_t)j * nb.blo_stride], hij = nb.bhi[(size_t)j * nb.blo_stride];
           // per axis "overlap or far", and far on at least one axis (see oracle_cell_list)

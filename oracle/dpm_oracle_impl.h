@@ -36,8 +36,12 @@ static inline void FN(cross3)(const REAL *a, const REAL *b, REAL *c) {
   c[1] = a[2] * b[0] - a[0] * b[2];
   c[2] = a[0] * b[1] - a[1] * b[0];
 }
+/* OpenCL normalize(): a zero vector is returned unchanged (measured on the reference's own runtime, NVIDIA OpenCL on the
+ * B200 box: oracle/cl_semantics_probe.cpp, profiles/r01_cl_semantics.log) -- reached when a vertex coincides with a vertex
+ * of another cell (attraction, solid angle). */
 static inline void FN(normalize3)(const REAL *a, REAL *u) {
   REAL n = RSQRT(FN(dot3)(a, a));
+  if (n == (REAL)0) { u[0] = u[1] = u[2] = (REAL)0; return; }
   u[0] = a[0] / n; u[1] = a[1] / n; u[2] = a[2] / n;
 }
 
@@ -429,7 +433,7 @@ void FN(oracle2d_forces)(int nc, int S, const int32_t *NV, const REAL *verts, RE
             if (dist < l0[ci]) {
               REAL ftmp = Kat / (REAL)n * dist / l0[ci];
               REAL nn = RSQRT(rx * rx + ry * ry);
-              fx += ftmp * (rx / nn); fy += ftmp * (ry / nn);
+              if (nn != (REAL)0) { fx += ftmp * (rx / nn); fy += ftmp * (ry / nn); } /* normalize(0) = 0 */
             }
           }
         }
@@ -457,8 +461,10 @@ void FN(oracle2d_forces)(int nc, int S, const int32_t *NV, const REAL *verts, RE
           REAL xij = dist / ((REAL)2 * r0[ci]);
           REAL ftmp = Kre * ((REAL)1 - xij);
           REAL nn = RSQRT(dx * dx + dy * dy);
-          fx += (REAL)0.5f * ftmp * (dx / nn);
-          fy += (REAL)0.5f * ftmp * (dy / nn);
+          if (nn != (REAL)0) { /* normalize(0) = 0 */
+            fx += (REAL)0.5f * ftmp * (dx / nn);
+            fy += (REAL)0.5f * ftmp * (dy / nn);
+          }
         }
       }
       Fo[2 * vi] = fx; Fo[2 * vi + 1] = fy;

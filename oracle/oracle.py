@@ -180,6 +180,25 @@ def run2d(verts2, NV, Ka, Kl, Kb, a0, l0, r0, Kre, Kat, PBC, L, nsteps, dt, whic
     return V, Fo
 
 
+def run2d_culled(verts2, NV, Ka, Kl, Kb, a0, l0, r0, Kre, Kat, PBC, L, nsteps, dt, dtype=np.float32, rebuild_every=1, K=64):
+    """nsteps of the CULLED 2D form (CPU cell list incl. the |d| > L wrap partners + literal kernels); usable at
+    config B's 4096 cells.  Candidate lists are rebuilt from the current fp32 AABBs every `rebuild_every` steps."""
+    V = np.array(verts2, dtype=dtype, copy=True)
+    nc = V.shape[0]
+    NVa = _arr(NV, nc, np.int32)
+    l0a = _arr(l0, nc, np.float32)
+    Fo = np.zeros_like(V)
+    cl = None
+    for s in range(int(nsteps)):
+        if cl is None or s % rebuild_every == 0:
+            lo, hi = aabb2d(V.astype(np.float32), NVa)
+            cl = cell_list(2, lo, hi, PBC, L, 0.3, float(l0a.max()) if Kat != 0 else 0.0, K, far2d=True)
+            assert cl["cand_count"].max() <= K, "2D candidate list overflow in the oracle"
+        Fo = forces2d(V, NVa, Ka, Kl, Kb, a0, l0, r0, Kre, Kat, PBC, L, cand_count=cl["cand_count"], cand=cl["cand"], dtype=dtype)
+        V += Fo * dtype(dt)
+    return V, Fo
+
+
 def aabb2d(verts2, NV):
     V = np.ascontiguousarray(verts2, np.float32)
     nc, S = V.shape[0], V.shape[1]

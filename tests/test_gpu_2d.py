@@ -153,3 +153,23 @@ def test_euler_update_and_skin_independence():
     assert h2.stats().rebuilds > h.stats().rebuilds
     assert np.array_equal(V1[m], V2[m]) and np.array_equal(F1[m], F2[m])
     h.close(); h2.close()
+
+
+def test_coincident_vertices_of_two_cells_stay_finite():
+    """Attraction pulls vertices of neighbouring cells together and in fp32 they can meet exactly (seen after ~530 steps
+    of config B): OpenCL normalize(0) = 0, so the pair adds nothing; the GPU must equal the oracle there, not NaN."""
+    O = _oracle()
+    d = H.config_test2d(32)
+    V = d["verts"].copy()
+    # move cell 1 so that one of its vertices lands exactly on a vertex of cell 0
+    shift = V[0, 3] - V[1, 11]
+    V[1, : d["nv"][1]] += shift
+    V[1, 11] = V[0, 3]
+    h = _handle(d)
+    for mask in (8, 31):
+        V1, F = _gpu(h, d, V, 1, mask, Kat=0.5)
+        Fref = O.forces2d(V, d["nv"], *[d[k] for k in PK], d["Kre"], 0.5, d["PBC"], d["L"], which=mask)
+        m = _real(d, F)
+        assert np.isfinite(Fref[m]).all() and np.isfinite(F[m]).all()
+        assert np.abs(F - Fref)[m].max() <= H.force_tol(Fref)
+    h.close()

@@ -231,3 +231,25 @@ def test_errors_and_validation():
         Dpm3D(2, 162, open_faces)
     assert e.value.code == 4
     h.close()
+
+
+def test_vertex_exactly_on_a_neighbour_vertex():
+    """normalize(0) = 0 in the reference's solid-angle sum (shaders/Cell3D_Kernel.cl:289-291): a vertex that coincides
+    with a vertex of the neighbour zeroes the terms of the faces at that corner.  The decomposition of the fast path
+    cannot express that, so the unit must take the literal sum and agree with the oracle (and stay finite)."""
+    O = _oracle()
+    d = H.config_test3d_cpp()
+    nv = d["nv"]
+    V = d["verts"].copy().reshape(d["nc"], nv, 4)
+    # translate cell 1 so that its vertex 40 sits exactly on vertex 12 of cell 0
+    V[1, :, :3] += (V[0, 12, :3] - V[1, 40, :3])[None, :]
+    V[1, 40, :3] = V[0, 12, :3]
+    V = V.reshape(-1, 4)
+    h = _handle(d)
+    _, F = _gpu_step(h, d, V, 1, 8)
+    args = (V, d["faces"], *[d[k] for k in PKEYS], d["Kre"], d["PBC"], d["L"])
+    Fref = O.forces3d(*args, which=8)
+    Fref64 = O.forces3d(*args, which=8, dtype=np.float64)
+    assert np.isfinite(F).all() and np.isfinite(Fref).all()
+    H.assert_forces_close(F, Fref, Fref64, what="repulsion with a coincident vertex")
+    h.close()

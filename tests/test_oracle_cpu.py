@@ -195,3 +195,26 @@ def test_f32_oracle_tracks_f64_oracle():
     V32, _ = O.run3d(*args, 20, 0.01)
     V64, _ = O.run3d(*args, 20, 0.01, dtype=np.float64)
     assert np.abs(V32[:, :3] - V64[:, :3]).max() < 5e-5
+
+
+def test_kat_coincident_vertices_follow_opencl_normalize_zero():
+    """Two vertices of different cells at exactly the same point: OpenCL's normalize() returns a zero vector unchanged
+    (measured on the reference's own runtime on the B200 box, profiles/r01_cl_semantics.log), so the attraction adds
+    nothing (shaders/Cell2D_kernel.cl:263-264) and the solid-angle terms of the faces at that corner are zero
+    (shaders/Cell3D_Kernel.cl:289-298) -- forces stay finite."""
+    d = _tissue2d(n=3, nv=24)
+    V = d["verts"].copy()
+    V[1, 5] = V[0, 17]  # cell 1's vertex 5 lands exactly on cell 0's vertex 17
+    args = (d["nv"], d["Ka"], d["Kl"], d["Kb"], d["a0"], d["l0"], d["r0"], 10.0, 0.5, 0, d["L"])
+    F = O.forces2d(V, *args, which=8)
+    assert np.isfinite(F).all()
+    # the coincident pair contributes nothing: same force as with the partner vertex far away, for that pair's share
+    V2 = V.copy()
+    V2[0, 17] += np.float32(1e-3)
+    F2 = O.forces2d(V2, *args, which=8)
+    assert np.abs(F[1, 5] - F2[1, 5]).max() < 2e-4  # coefficient ~ Kat/n * d/l0 with d = 1e-3
+    t = _tissue3d(n=2)
+    W = t["verts"].copy().reshape(t["nc"], -1, 4)
+    W[1, 7, :3] = W[0, 30, :3]  # a vertex of cell 1 exactly on a vertex of cell 0
+    F3 = O.forces3d(W.reshape(-1, 4), t["faces"], *[t[k] for k in PK3], 25.0, 0, t["L"], which=8)
+    assert np.isfinite(F3).all()
