@@ -46,7 +46,13 @@ extern "C" {
 #define DPM3D_AREA 2u   /* SurfaceAreaForceUpdate  shaders/Cell3D_Kernel.cl:114-177 */
 #define DPM3D_STICK 4u  /* StickToSurface          shaders/Cell3D_Kernel.cl:180-247 */
 #define DPM3D_REPEL 8u  /* RepellingForces         shaders/Cell3D_Kernel.cl:251-310 */
-#define DPM3D_ALL 15u
+#define DPM3D_ALL 15u   /* the kernels the reference host enqueues (src/Tissue3D.cpp:372-423): the default mask */
+/* AllVertAttraction (shaders/Cell3D_Kernel.cl:313-364): vertex-vertex attraction between cells, strength Kat.  The
+ * reference compiles it but never enqueues it, so it is NOT part of the default mask: a caller opts in
+ * with dpm3d_set_force_mask(h, DPM3D_ALL | DPM3D_ATTRACT) and a non-zero Kat; it then runs between RepellingForces
+ * and EulerPosition.  Evaluated in gather form (each vertex sums what it adds to itself and what the other vertex's
+ * work-item would scatter onto it), so ghost cells of a sharded run stay read-only. */
+#define DPM3D_ATTRACT 16u
 
 #define DPM2D_AREA 1u      /* AreaForceUpdates       shaders/Cell2D_kernel.cl:13-42   */
 #define DPM2D_PERIMETER 2u /* PerimeterForceUpdates  shaders/Cell2D_kernel.cl:92-119  */
@@ -123,8 +129,8 @@ int dpm3d_upload(dpm3d_t *h, const float *verts4, const float *Kv, const float *
 int dpm3d_upload_device(dpm3d_t *h, const float *verts4_dev, const float *Kv, const float *Ka, const float *Ks,
                         const float *v0, const float *a0, const float *l0);
 /* nsteps of {ClearForces, Volume, SurfaceArea, StickToSurface, Repelling, EulerPosition}
- * (src/Tissue3D.cpp:372-423) fused; asynchronous.  Kat is accepted for interface fidelity;
- * the reference never launches AllVertAttraction. */
+ * (src/Tissue3D.cpp:372-423) fused; asynchronous.  Kat is only used when the force mask contains DPM3D_ATTRACT
+ * (the reference never launches AllVertAttraction, SURVEY F12: by default Kat has no effect, as in the reference). */
 int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, float L);
 int dpm3d_sync(dpm3d_t *h);
 /* verts4 and/or forces4 may be NULL. forces4 = forces of the last executed step. */

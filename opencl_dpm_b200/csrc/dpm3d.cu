@@ -171,6 +171,7 @@ NbrBuffers nbr_buffers(dpm3d_ctx *h, int pbc, float L) {
   nb.gid = h->gid;
   nb.pbc = pbc; nb.L = L; nb.skin_rel = h->skin_rel; nb.range = 0.0f; nb.far2d = 0;
   nb.range_from_bounds = 1; nb.range_scale = RANGE_HEADROOM;
+  nb.att_pad_scale = h->att_active ? ATT_REACH / RANGE_HEADROOM * 1.0001f : 0.0f;  // range >= ATT_REACH * max l0
   return nb;
 }
 
@@ -178,11 +179,13 @@ int alloc_units(dpm3d_ctx *h, int per_cell) {
   if (h->unit_rec && per_cell <= h->unit_per_cell) return DPM_OK;
   if (h->unit_rec) cudaFree(h->unit_rec);
   if (h->unit_w) cudaFree(h->unit_w);
-  h->unit_rec = nullptr; h->unit_w = nullptr;
+  if (h->unit_att) cudaFree(h->unit_att);
+  h->unit_rec = nullptr; h->unit_w = nullptr; h->unit_att = nullptr;
   h->unit_per_cell = per_cell;
   h->unit_cap = (int)std::min<long long>((long long)h->nc * per_cell, 1ll << 30);
   DPM_CUDA_TRY(cudaMalloc(&h->unit_rec, sizeof(int2) * (size_t)h->unit_cap));
   DPM_CUDA_TRY(cudaMalloc(&h->unit_w, sizeof(float) * (size_t)h->unit_cap));
+  if (h->mask & DPM3D_ATTRACT) DPM_CUDA_TRY(cudaMalloc(&h->unit_att, sizeof(float4) * (size_t)h->unit_cap));
   return DPM_OK;
 }
 
@@ -307,7 +310,7 @@ int dpm3d_destroy(dpm3d_t *h) {
   shard_free(h);
   void *ptrs[] = {h->pos[0], h->pos[1], h->force, h->bnd[0], h->bnd[1], h->cellA, h->cellB, h->faces, h->ring_nbr, h->ring_face,
                   h->valence, h->face_adj, h->ring_tab, h->ring_end, h->dir_table, h->st, h->bbox_lo, h->bbox_hi, h->bin_id, h->order, h->bin_count, h->bin_start, h->cand_count,
-                  h->cand, h->partial, h->chunk_sum, h->unit_rec, h->unit_w, h->unit_base, h->unit_cnt, h->flag[0], h->flag[1], h->unit_idx};
+                  h->cand, h->partial, h->chunk_sum, h->unit_rec, h->unit_w, h->unit_att, h->unit_base, h->unit_cnt, h->flag[0], h->flag[1], h->unit_idx};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (h->h_cell) cudaFreeHost(h->h_cell);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -347,7 +350,11 @@ int dpm3d_set_compat(dpm3d_t *h, int stale_volume_from_face) {
 
 int dpm3d_set_force_mask(dpm3d_t *h, unsigned mask) {
   if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
-  h->mask = mask & DPM3D_ALL;
+  h->mask = mask & (DPM3D_ALL | DPM3D_ATTRACT);
+  if ((h->mask & DPM3D_ATTRACT) && !h->unit_att) {  // the attraction term of every unit
+    DeviceGuard guard(h->device);
+    DPM_CUDA_TRY(cudaMalloc(&h->unit_att, sizeof(float4) * (size_t)h->unit_cap));
+  }
   return DPM_OK;
 }
 
@@ -368,7 +375,7 @@ static int upload_common(dpm3d_t *h, const float *verts4, bool on_device, const 
   DPM_CUDA_TRY(cudaMemsetAsync(h->st, 0, sizeof(NbrState), h->stream));
   // walk-start table of the fast contact evaluation, from cell 0's current shape
   dpm3d_dirtable_kernel<<<DIR_N * DIR_N, STEP_THREADS, 0, h->stream>>>(h->pos[0], h->faces, h->nv, h->nf, h->dir_table);
-  dpm3d_bounds_kernel<<<h->nc, STEP_THREADS, h->smem, h->stream>>>(h->pos[0], h->bnd[0], h->flag[0], h->nc, cell_topo(h));
+  dpm3d_bounds_kernel<<<h->nc, STEP_THREADS, h->smem, h->stream>>>(h->pos[0], h->bnd[0], h->flag[0], h->nc, cell_topo(h), h->cellB);
   DPM_CUDA_TRY(cudaGetLastError());
   h->stats.launches += 1;
   h->stats.steps = 0; h->stats.rebuilds = 0; h->stats.contact_evals = 0;  // per-upload counters (launches stay cumulative)
@@ -404,7 +411,8 @@ int dpm3d_rebuild_neighbors(dpm3d_t *h, int pbc, float L) {
 }
 
 int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, float L) {
-  (void)Kat;  // AllVertAttraction is never enqueued by the reference host
+  // AllVertAttraction is never enqueued by the reference host: Kat only acts under DPM3D_ATTRACT
+  const bool attract = (h->mask & DPM3D_ATTRACT) && Kat != 0.0f;  // the kernel returns at once when Kat == 0 (:318-319)
   if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
   if (nsteps <= 0) return fail(DPM_ERR_INVALID_ARGUMENT, "nsteps must be positive");                          // src/Tissue3D.cpp:123-126
   if (!(dt > 0.0f) || dt > 0.1f) return fail(DPM_ERR_INVALID_ARGUMENT, "dt must be positive and reasonable");  // :127-131
@@ -417,14 +425,16 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
   p.cand_count = h->cand_count; p.cand = h->cand; p.K = h->K;
   p.bbox_lo = h->bbox_lo; p.bbox_hi = h->bbox_hi; p.st = h->st;
   p.unit_idx = h->unit_idx;
-  p.unit_rec = h->unit_rec; p.unit_w = h->unit_w; p.unit_base = h->unit_base; p.unit_cnt = h->unit_cnt; p.unit_cap = h->unit_cap;
+  p.unit_rec = h->unit_rec; p.unit_w = h->unit_w; p.unit_att = h->unit_att; p.unit_base = h->unit_base; p.unit_cnt = h->unit_cnt; p.unit_cap = h->unit_cap;
   const bool repel = (h->mask & DPM3D_REPEL) && Kre != 0.0f;
-  p.nc = h->nc; p.nv = h->nv; p.nf = h->nf; p.dt = dt; p.Kc = Kre; p.pbc = pbc; p.L = L; p.mask = h->mask;
+  p.nc = h->nc; p.nv = h->nv; p.nf = h->nf; p.dt = dt; p.Kc = Kre; p.pbc = pbc; p.L = L;
+  p.mask = attract ? h->mask : (h->mask & ~DPM3D_ATTRACT);
+  p.Kat = attract ? Kat : 0.0f;
   p.stale_from = h->stale_from;
-  if (pbc != h->last_pbc || L != h->last_L) {  // the lists depend on the box: rebuild when the caller changed it
+  if (pbc != h->last_pbc || L != h->last_L || attract != h->att_active) {  // the lists depend on the box: rebuild when the caller changed it
     static const int one = 1;
     DPM_CUDA_TRY(cudaMemcpyAsync(&h->st->rebuild, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    h->last_pbc = pbc; h->last_L = L;
+    h->last_pbc = pbc; h->last_L = L; h->att_active = attract;
   }
   // DPM_TRACE: device time of each kernel of ONE timestep in the middle of the call (events on the stream)
   static const bool trace = getenv("DPM_TRACE") != nullptr;
@@ -444,7 +454,7 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
     p.bnd_in = h->bnd[h->cur]; p.bnd_out = h->bnd[h->cur ^ 1];
     p.flag_in = h->flag[h->cur]; p.flag_out = h->flag[h->cur ^ 1];
     p.force_out = (s == nsteps - 1) ? h->force : nullptr;  // forces are only read back after the last step (:425-434)
-    if (repel) {
+    if (repel || attract) {
       DPM_CUDA_TRY(launch_pdl(dpm3d_units_kernel, h->nc, UNITS_THREADS, 0, h->stream, p));
       if (tr) cudaEventRecord(tev[2], h->stream);
       DPM_CUDA_TRY(launch_pdl(dpm3d_contact_kernel, h->contact_grid, CONTACT_THREADS, 0, h->stream, p));
@@ -463,7 +473,7 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
     for (auto &e : tev) cudaEventDestroy(e);
   }
   h->stats.steps += (uint64_t)nsteps;
-  h->stats.launches += (repel ? 4ull : 2ull) * (uint64_t)nsteps;
+  h->stats.launches += ((repel || attract) ? 4ull : 2ull) * (uint64_t)nsteps;
   return DPM_OK;
 }
 

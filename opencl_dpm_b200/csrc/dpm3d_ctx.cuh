@@ -31,6 +31,7 @@ struct dpm3d_ctx {
   unsigned *unit_idx = nullptr;                 // per-vertex (offset << 8 | count) into the cell's unit range
   int2 *unit_rec = nullptr;  // contact-unit queue (dpm3d_units_kernel -> dpm3d_contact_kernel -> dpm3d_step_kernel)
   float *unit_w = nullptr;
+  float4 *unit_att = nullptr;  // allocated when DPM3D_ATTRACT is selected
   int *unit_base = nullptr, *unit_cnt = nullptr;
   int unit_cap = 0, unit_per_cell = 0;
   int contact_grid = 0;
@@ -51,6 +52,7 @@ struct dpm3d_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_up = nullptr;
   float4 *h_cell = nullptr;  // pinned staging for per-cell parameters
   dpm_stats_t stats{};
+  bool att_active = false;  // the neighbour lists in use were built with the attraction reach
   int last_pbc = -1;
   float last_L = -1.f;
   int stale_from = -1;

@@ -54,12 +54,14 @@ struct Step3DParams {
   // per-cell contiguous range [unit_base[ci], +unit_cnt[ci]) of one global list, evaluated by dpm3d_contact_kernel
   int2 *__restrict__ unit_rec;
   float *__restrict__ unit_w;
+  float4 *__restrict__ unit_att;  // DPM3D_ATTRACT: the unit's AllVertAttraction force on its vertex (else unused)
   int *__restrict__ unit_base;
   int *__restrict__ unit_cnt;
   int unit_cap;
   int nc;  // cells stepped by this launch (owned)
   int nv, nf;
   float dt, Kc;
+  float Kat;  // != 0 only when DPM3D_ATTRACT is in the mask
   int pbc;
   float L;
   unsigned mask;
@@ -90,6 +92,9 @@ constexpr int BND = 4;              // float4 per cell in the bounds arrays:
 // box / sphere gets w_ref = W = 0 from it and is culled exactly.
 constexpr float CONTACT_PAD = 0.34f;
 constexpr float RANGE_HEADROOM = 1.25f;  // lists are built for pads up to 1.25x the largest current one
+// AllVertAttraction reaches 2 * l0 of either cell (shaders/Cell3D_Kernel.cl:350): a vertex can only take part if it is
+// within ATT_REACH * max(l0_i, l0_j) of the other cell's box and bounding sphere (the 1e-3 covers fp32 rounding of the test)
+constexpr float ATT_REACH = 2.002f;
 constexpr int RING_MAX = 6;              // edge-adjacency rings examined around the radially hit face
 constexpr int RING_TAB = 64;             // 1 + 3 + 6 + 9 + 12 + 15 + 18 = 64 faces: one 64-bit hit mask
 constexpr int DIR_N = 16;                // octahedral map resolution
@@ -363,7 +368,7 @@ constexpr int UNITS_THREADS = 256;
 constexpr int UNITS_VPT = 4;  // nv <= 1024
 constexpr int UNITS_KMAX = 128;
 
-static __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams P) {
+static __global__ void __launch_bounds__(UNITS_THREADS, 4) dpm3d_units_kernel(Step3DParams P) {
   __shared__ float4 sLo[UNITS_KMAX], sHi[UNITS_KMAX], sSph[UNITS_KMAX];
   __shared__ int sCand[UNITS_KMAX];
   __shared__ int sWarp[UNITS_THREADS / 32];
@@ -373,6 +378,8 @@ static __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3
   griddep_launch();
   // state of the previous timestep's step kernel (complete before the kernel ahead of this one started): read it now
   const float4 bi0 = P.bnd_in[BND * (size_t)ci], bi1 = P.bnd_in[BND * (size_t)ci + 1], bi2 = P.bnd_in[BND * (size_t)ci + 2];
+  const bool att = (P.mask & DPM3D_ATTRACT) != 0;
+  const float l0i = att ? P.bnd_in[BND * (size_t)ci + 3].w : 0.0f;
   float4 myp[UNITS_VPT];
 #pragma unroll
   for (int j = 0; j < UNITS_VPT; j++) {
@@ -392,15 +399,34 @@ static __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3
       sh.z = P.L * roundf((bi2.z - bj2.z) / P.L);
     }
     // padded, shifted bounding box / sphere of cj: outside them the reference's formula gives exactly zero
-    const float pad = bj1.w;  // CONTACT_PAD * (longest edge of cj)
-    const float4 lo = make_float4((bj0.x + sh.x) - pad, (bj0.y + sh.y) - pad, (bj0.z + sh.z) - pad, 0.f);
-    const float4 hi = make_float4((bj1.x + sh.x) + pad, (bj1.y + sh.y) + pad, (bj1.z + sh.z) + pad, 0.f);
+    float pad = bj1.w;  // CONTACT_PAD * (longest edge of cj)
+    bool nocull = false;
+    if (att) {
+      // AllVertAttraction pairs lie within 2 * max(l0_i, l0_j) of each other (:350).  It takes the minimum image of every
+      // vertex pair (:338-343); that is the image of the COM shift unless the box is so small that a second image of cj can
+      // come within reach of this cell as well: then every vertex is kept for cj (the evaluation itself is literal).
+      pad = fmaxf(pad, ATT_REACH * fmaxf(l0i, P.bnd_in[BND * (size_t)cj + 3].w));
+      if (P.pbc) {
+        const float dmx = fmaxf(fabsf((bj1.x + sh.x) - bi0.x), fabsf(bi1.x - (bj0.x + sh.x)));
+        const float dmy = fmaxf(fabsf((bj1.y + sh.y) - bi0.y), fabsf(bi1.y - (bj0.y + sh.y)));
+        const float dmz = fmaxf(fabsf((bj1.z + sh.z) - bi0.z), fabsf(bi1.z - (bj0.z + sh.z)));
+        nocull = !(fmaxf(dmx, fmaxf(dmy, dmz)) + pad < P.L);
+      }
+    }
+    float4 lo = make_float4((bj0.x + sh.x) - pad, (bj0.y + sh.y) - pad, (bj0.z + sh.z) - pad, 0.f);
+    float4 hi = make_float4((bj1.x + sh.x) + pad, (bj1.y + sh.y) + pad, (bj1.z + sh.z) + pad, 0.f);
+    const float rs = sqrtf(bj0.w) + pad;
+    float4 sph = make_float4(bj2.x + sh.x, bj2.y + sh.y, bj2.z + sh.z, rs * rs * 1.0001f + 1e-30f);
+    if (nocull) {
+      lo = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+      hi = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
+      sph.w = INFINITY;
+    }
     const bool ov = !(lo.x > bi1.x || hi.x < bi0.x || lo.y > bi1.y || hi.y < bi0.y || lo.z > bi1.z || hi.z < bi0.z);
     sCand[k] = ov ? cj : -1;
     sLo[k] = lo;
     sHi[k] = hi;
-    const float rs = sqrtf(bj0.w) + pad;
-    sSph[k] = make_float4(bj2.x + sh.x, bj2.y + sh.y, bj2.z + sh.z, rs * rs * 1.0001f + 1e-30f);
+    sSph[k] = sph;
     nact += ov ? 1 : 0;
   }
   if (__syncthreads_or(nact) == 0) {  // no neighbour's box reaches this cell
@@ -501,6 +527,7 @@ static __global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(S
     const float4 p = P.pos_in[rec.x];
     const float4 bi2 = P.bnd_in[BND * (size_t)ci + 2];
     const float4 bj1 = P.bnd_in[BND * (size_t)cj + 1], bj2 = P.bnd_in[BND * (size_t)cj + 2], bj3 = P.bnd_in[BND * (size_t)cj + 3];
+    const bool att = (P.mask & DPM3D_ATTRACT) != 0;
     float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
     if (P.pbc) {  // shift = L * round((COMi - COMJ) / L)   (:277-281)
       sh.x = P.L * roundf((bi2.x - bj2.x) / P.L);
@@ -509,14 +536,64 @@ static __global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(S
     }
     const float4 *Vj = P.pos_in + (size_t)cj * nv;
     const bool star = bj3.y != 0.0f;  // neighbour star-shaped about its COM (checked by its owner's epilogue)
+    // With the attraction on, the units kernel admits vertices within the (larger) attraction pad: the contact term is
+    // evaluated only for those that pass the units kernel's test with the CONTACT pad (same expressions), the others get
+    // w = 0 exactly as if they had been culled.
+    bool contact = active;
+    if (att) {
+      contact = active && (P.mask & DPM3D_REPEL) && P.Kc != 0.0f;
+      const float4 bj0 = P.bnd_in[BND * (size_t)cj];
+      const float pad = bj1.w;
+      const float lx = (bj0.x + sh.x) - pad, ly = (bj0.y + sh.y) - pad, lz = (bj0.z + sh.z) - pad;
+      const float hx = (bj1.x + sh.x) + pad, hy = (bj1.y + sh.y) + pad, hz = (bj1.z + sh.z) + pad;
+      const float rs = sqrtf(bj0.w) + pad;
+      const float dx = p.x - (bj2.x + sh.x), dy = p.y - (bj2.y + sh.y), dz = p.z - (bj2.z + sh.z);
+      contact = contact && !(p.x < lx || p.x > hx || p.y < ly || p.y > hy || p.z < lz || p.z > hz) &&
+                (dx * dx + dy * dy + dz * dz) <= rs * rs * 1.0001f + 1e-30f;
+    }
     float w = 0.0f;
-    int why = winding_fast(P, active && star, Vj, sh, p, f3(bj2.x + sh.x, bj2.y + sh.y, bj2.z + sh.z), bj1.w, w, g, gshift);
-    if (active && !star) why = -1;
-    if (active && why != 0) {  // group-uniform branch
+    int why = winding_fast(P, contact && star, Vj, sh, p, f3(bj2.x + sh.x, bj2.y + sh.y, bj2.z + sh.z), bj1.w, w, g, gshift);
+    if (contact && !star) why = -1;
+    if (contact && why != 0) {  // group-uniform branch
       w = winding_literal(Vj, P.faces, P.nf, sh, p, g, gmask);
       if (g == 0) { atomicAdd(&P.st->literal_evals, 1ull); atomicAdd(&P.st->fallback_why[why < 0 ? 0 : why], 1ull); }
     }
-    if (active && g == 0) P.unit_w[u] = w;
+    if (active && g == 0) P.unit_w[u] = contact ? w : 0.0f;
+    if (att) {
+      // AllVertAttraction (shaders/Cell3D_Kernel.cl:313-364) in gather form: what this vertex's work-item adds to itself
+      // (rest length l0[ci]) plus what the work-item of every vertex vj of cj scatters onto it (rest length l0[cj]; its
+      // delta is exactly -delta and its distance exactly dist).  The group's 8 lanes take different vj.
+      const float l0i = fmaxf(P.bnd_in[BND * (size_t)ci + 3].w, 1e-12f), l0j = fmaxf(bj3.w, 1e-12f);
+      float ax = 0.0f, ay = 0.0f, az = 0.0f;
+      if (active) {
+        for (int vj = g; vj < nv; vj += UNIT_LANES) {
+          const float4 q = __ldg(Vj + vj);
+          float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
+          if (P.pbc) {  // :338-343
+            dx -= P.L * roundf(dx / P.L);
+            dy -= P.L * roundf(dy / P.L);
+            dz -= P.L * roundf(dz / P.L);
+          }
+          const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+          float s = 0.0f;
+          if (dist > 1e-12f) {  // :350
+            if (dist < l0i * 2.0f) s += P.Kat * 0.5f * (dist / l0i - 1.0f);
+            if (dist < l0j * 2.0f) s += P.Kat * 0.5f * (dist / l0j - 1.0f);
+          }
+          if (s != 0.0f) {
+            const float r = s / dist;
+            ax -= r * dx; ay -= r * dy; az -= r * dz;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = UNIT_LANES / 2; o > 0; o >>= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, o);
+        ay += __shfl_xor_sync(0xffffffffu, ay, o);
+        az += __shfl_xor_sync(0xffffffffu, az, o);
+      }
+      if (active && g == 0) P.unit_att[u] = make_float4(ax, ay, az, 0.0f);
+    }
   }
 }
 
@@ -536,7 +613,7 @@ __device__ __forceinline__ bool face_sees_centre(float4 P0, float3 n, float nn, 
 // star-shape flag.  Used by the bounds kernel (after an upload) and by the step kernel's epilogue (for the NEW
 // positions).  Block of STEP_THREADS threads; sWide: max(nv, ceil(nf/2)) float4 of scratch.  Every thread passes the partial vertex
 // sum and partial AABB of the vertices it staged / integrated (tid, tid + STEP_THREADS, ...).
-//   bnd[0] = (lo.xyz, r2max)   bnd[1] = (hi.xyz, pad)   bnd[2] = (com.xyz, volume)   bnd[3] = (r2min, star, vol_prev, 0)
+//   bnd[0] = (lo.xyz, r2max)   bnd[1] = (hi.xyz, pad)   bnd[2] = (com.xyz, volume)   bnd[3] = (r2min, star, vol_prev, l0)
 // ---------------------------------------------------------------------------------
 constexpr int STEP_THREADS = 128;
 constexpr int STEP_WARPS = STEP_THREADS / 32;
@@ -563,7 +640,7 @@ struct VertPartial {  // per-thread partials over the thread's own vertices
   }
 };
 
-__device__ __forceinline__ void cell_scalars(const float4 *sP, float4 *sWide, const CellTopo &T, VertPartial vp, float vol_prev,
+__device__ __forceinline__ void cell_scalars(const float4 *sP, float4 *sWide, const CellTopo &T, VertPartial vp, float vol_prev, const float4 *cellB_ci,
                                              float4 *bnd_cell, unsigned char *flag_cell, const float4 *bbox_lo, const float4 *bbox_hi,
                                              NbrState *st) {
   __shared__ float sRed[STEP_WARPS][12];
@@ -664,7 +741,7 @@ __device__ __forceinline__ void cell_scalars(const float4 *sP, float4 *sWide, co
     bnd_cell[0] = make_float4(l[0], l[1], l[2], rr);
     bnd_cell[1] = make_float4(h[0], h[1], h[2], pad);
     bnd_cell[2] = make_float4(com.x, com.y, com.z, sSc[3]);
-    bnd_cell[3] = make_float4(rm, star ? 1.f : 0.f, vol_prev, 0.f);
+    bnd_cell[3] = make_float4(rm, star ? 1.f : 0.f, vol_prev, cellB_ci->y);  // l0 travels with the bounds (ghost cells have no parameters)
     if (st) {  // neighbour-list validity
       const float4 bl = *bbox_lo, bh = *bbox_hi;
       if (l[0] < bl.x || l[1] < bl.y || l[2] < bl.z || h[0] > bh.x || h[1] > bh.y || h[2] > bh.z) st->rebuild = 1;
@@ -674,7 +751,7 @@ __device__ __forceinline__ void cell_scalars(const float4 *sP, float4 *sWide, co
 }
 
 static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_bounds_kernel(const float4 *pos, float4 *bnd, unsigned char *flags, int nc,
-                                                                           CellTopo T) {
+                                                                           CellTopo T, const float4 *cellB) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 *sP = reinterpret_cast<float4 *>(smem_raw);
   float4 *sWide = sP + T.nv;  // same carve-up as the step kernel (sP | sF | sFlag)
@@ -687,7 +764,7 @@ static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_bounds_kernel(const
     vp.add(p);
   }
   __syncthreads();
-  cell_scalars(sP, sWide, T, vp, 0.0f, bnd + BND * (size_t)ci, flags + (size_t)ci * T.nf, nullptr, nullptr, nullptr);
+  cell_scalars(sP, sWide, T, vp, 0.0f, cellB + ci, bnd + BND * (size_t)ci, flags + (size_t)ci * T.nf, nullptr, nullptr, nullptr);
 }
 
 // Walk-start table of the fast contact evaluation: for the direction of each octahedral texel, the face of cell 0 whose
@@ -886,8 +963,11 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
   // ---- Euler update (EulerPosition :380), outputs ----------------------------------------------------------
   // The contact weights are the only input from this timestep's units / contact kernels: everything above overlaps them.
   griddep_wait();
-  const int ucnt = doRep ? P.unit_cnt[ci] : 0;
-  const float *uw = P.unit_w + (doRep ? P.unit_base[ci] : 0);
+  const bool doAtt = (P.mask & DPM3D_ATTRACT) && P.Kat != 0.0f;
+  const int ucnt = (doRep || doAtt) ? P.unit_cnt[ci] : 0;
+  const int ubase = (doRep || doAtt) ? P.unit_base[ci] : 0;
+  const float *uw = P.unit_w + ubase;
+  const float4 *ua = P.unit_att + ubase;
   VertPartial vp;
   vp.init();
   for (int v = tid; v < nv; v += STEP_THREADS) {
@@ -899,9 +979,12 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
       const int un = ui & 0xffu, uo = ui >> 8;
       float3 dir = f3(0.f, 0.f, 0.f);
       bool have = false;
+      if (doAtt)  // AllVertAttraction (:313-364): the units' gathered vertex-vertex terms
+        DPM_UNROLL(1)
+        for (int u = uo; u < uo + un; u++) { const float4 a = ua[u]; F.x += a.x; F.y += a.y; F.z += a.z; }
       for (int u = uo; u < uo + un; u++) {
         const float wn = uw[u];
-        if (!(fabsf(wn) < 1e-6f)) {  // :302-308
+        if (doRep && !(fabsf(wn) < 1e-6f)) {  // :302-308
           if (!have) {
             const float3 d = f3(com.x - np.x, com.y - np.y, com.z - np.z);
             const float r = rsqrtf(dot3(d, d));
@@ -926,7 +1009,7 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
   // ---- next step's per-cell scalars from the NEW positions --------------------------------------------------
   CellTopo T;
   T.faces = P.faces; T.ring_nbr = P.ring_nbr; T.valence = P.valence; T.ring_stride = P.ring_stride; T.nv = nv; T.nf = nf;
-  cell_scalars(sP, sF, T, vp, bi2.w, P.bnd_out + BND * (size_t)ci, P.flag_out + (size_t)ci * nf, P.bbox_lo + ci, P.bbox_hi + ci, P.st);
+  cell_scalars(sP, sF, T, vp, bi2.w, P.cellB + ci, P.bnd_out + BND * (size_t)ci, P.flag_out + (size_t)ci * nf, P.bbox_lo + ci, P.bbox_hi + ci, P.st);
   if (tid == 0) bulk_wait_all();  // the bulk store has read sP (and landed) before the CTA's shared memory is released
 }
 

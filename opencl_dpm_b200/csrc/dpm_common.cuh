@@ -69,6 +69,7 @@ struct NbrBuffers {
   float range;        // explicit interaction range (range_from_bounds == 0)
   int range_from_bounds;  // 1: range = range_scale * max_c bhi[c].w (per-cell contact pad), recorded in st->range
   float range_scale;
+  float att_pad_scale;  // 3D vertex-vertex attraction on: a cell's pad counts as max(pad, att_pad_scale * l0), l0 = blo[3].w
   int far2d;
   int *ext_list;  // far2d: [nc] scratch, the cells near the global extremes (filled by the rebuild kernel)
 };

@@ -86,7 +86,7 @@ __host__ __device__ inline size_t msg_off_pos(int C) { return msg_off_bnd(C) + s
 __host__ __device__ inline size_t msg_size(int C, int nv) { return msg_off_pos(C) + sizeof(float4) * (size_t)nv * C; }
 
 // ---- 1. per-rank summary -------------------------------------------------------------------------------------
-__global__ void shard_prepare_kernel(const float4 *bnd, int n_own, const NbrState *st, float *out) {
+__global__ void shard_prepare_kernel(const float4 *bnd, int n_own, const NbrState *st, float *out, float att_pad_scale) {
   __shared__ float s[8][4];
   float rlo = INFINITY, rhi = -INFINITY, ext = 0.f, pad = 0.f;
   for (int c = threadIdx.x; c < n_own; c += blockDim.x) {
@@ -94,6 +94,7 @@ __global__ void shard_prepare_kernel(const float4 *bnd, int n_own, const NbrStat
     rlo = fminf(rlo, lo.x); rhi = fmaxf(rhi, hi.x);
     ext = fmaxf(ext, fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z)));
     pad = fmaxf(pad, hi.w);
+    if (att_pad_scale > 0.0f) pad = fmaxf(pad, att_pad_scale * bnd[BND * (size_t)c + 3].w);  // attraction reach (see NbrBuffers)
   }
   rlo = warp_min(rlo); rhi = warp_max(rhi); ext = warp_max(ext); pad = warp_max(pad);
   const int w = threadIdx.x >> 5;
@@ -213,7 +214,8 @@ int shard_exchange(dpm3d_ctx *h, int pbc, float L) {
   Nccl &N = nccl();
   ncclComm_t comm = static_cast<ncclComm_t>(h->comm);
   float4 *pos = h->pos[h->cur], *bnd = h->bnd[h->cur];
-  shard_prepare_kernel<<<1, 256, 0, h->stream>>>(bnd, h->nc, h->st, h->gather_send);
+  shard_prepare_kernel<<<1, 256, 0, h->stream>>>(bnd, h->nc, h->st, h->gather_send,
+                                                 h->att_active ? ATT_REACH / RANGE_HEADROOM * 1.0001f : 0.0f);
   DPM_NCCL_TRY(N.AllGather(h->gather_send, h->gather_all, GATHER, ncclFloat, comm, h->stream));
   shard_select_kernel<<<1, 256, 0, h->stream>>>(bnd, h->nc, h->st, h->sd, h->gather_all, h->rank, h->nranks, h->npeers, h->peer[0],
                                                  h->npeers > 1 ? h->peer[1] : -1, h->sendlist[0], h->sendlist[1], h->ghost_cap,

@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(RB_THREADS) nbr_rebuild_kernel(NbrBuffers nb) 
       float4 lo = nb.blo[(size_t)c * nb.blo_stride], hi = nb.bhi[(size_t)c * nb.blo_stride];
       const float l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
       padmx = fmaxf(padmx, hi.w);
+      if (nb.att_pad_scale > 0.0f) padmx = fmaxf(padmx, nb.att_pad_scale * nb.blo[(size_t)c * nb.blo_stride + 3].w);
 #pragma unroll
       for (int d = 0; d < 3; d++) {
         if (d < nb.nd) {

@@ -129,6 +129,11 @@ void Tissue3D::CLEulerUpdate(int nsteps, float dt) {
       dev->ncells = NCELLS;
       dev->faces = faces;
     }
+    // AllVertAttraction (shaders/Cell3D_Kernel.cl:313-364) is compiled but never enqueued by the reference, whatever Kat
+    // is, and `attractionMethod` ("General", src/Tissue3D.cpp:30) is never read.  Default behaviour is
+    // therefore unchanged; setting attractionMethod = "AllVertAttraction" opts in to that kernel with strength Kat.
+    const unsigned mask = DPM3D_ALL | (attractionMethod == "AllVertAttraction" ? DPM3D_ATTRACT : 0u);
+    if (dpm3d_set_force_mask(dev->h, mask) != DPM_OK) throw std::runtime_error(last_error());
     float loop_ms = 0.0f;
     const int rc = dpm3d_euler_update(dev->h, verts.data(), forces.data(), Kv.data(), Ka.data(), Ks.data(), v0.data(),
                                       a0.data(), l0.data(), nsteps, dt, Kre, Kat, PBC, L, &loop_ms);

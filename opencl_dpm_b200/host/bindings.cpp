@@ -48,6 +48,8 @@ PYBIND11_MODULE(clDPM, m) {
       .def(py::init<std::vector<Cell3D>, float>())
       .def_readwrite("Kre", &Tissue3D::Kre)
       .def_readwrite("Kat", &Tissue3D::Kat)
+      // extension: "General" (default, reference behaviour: Kat is inert in 3D) or "AllVertAttraction"
+      .def_readwrite("attractionMethod", &Tissue3D::attractionMethod)
       .def_readwrite("Cells", &Tissue3D::Cells)
       .def_readonly("NCELLS", &Tissue3D::NCELLS)
       .def_readonly("L", &Tissue3D::L)

@@ -293,6 +293,40 @@ void FN(oracle3d_forces_range)(int nc, int nv, int nf, const uint32_t *faces, co
                      c0, c1, -1, NULL);
 }
 
+/* shaders/Cell3D_Kernel.cl:313-364  AllVertAttraction, literally (scatter form: the work-item of vertex (ci,vi)
+ * visits every vertex (cj,vj) of every other cell and adds -t to its own force and +t to the OTHER vertex's force,
+ * with the rest length l0[ci] of ITS cell).  The reference host never enqueues this kernel, so the
+ * default product path does not run it either; it is the §8(f) rank-1 "next" row, enabled by DPM3D_ATTRACT.
+ * Serial here (the scatter would race under OpenMP); forces are ACCUMULATED into `forces`.
+ * The product evaluates the equivalent gather form  F_i -= sum_j [g(d,l0_i) + g(d,l0_j)] * delta/d  (the second term
+ * is what vertex j's work-item scatters onto i: its delta is exactly -delta and its distance exactly d). */
+void FN(oracle3d_attract)(int nc, int nv, const REAL *verts, REAL *forces, const REAL *l0, REAL L, int PBC, REAL Kat) {
+  if (Kat == (REAL)0.0) return; /* :318-319 */
+  for (int ci = 0; ci < nc; ci++) for (int vi = 0; vi < nv; vi++) {
+    const size_t i = (size_t)ci * nv + vi;
+    const REAL *p1 = verts + 4 * i;
+    for (int cj = 0; cj < nc; cj++) {
+      if (cj == ci) continue;
+      for (int vj = 0; vj < nv; vj++) {
+        const size_t j = (size_t)cj * nv + vj;
+        const REAL *p2 = verts + 4 * j;
+        REAL delta[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+        if (PBC) for (int d = 0; d < 3; d++) delta[d] -= L * RROUND(delta[d] / L); /* :338-343 */
+        REAL dist = RSQRT(FN(dot3)(delta, delta));
+        REAL L0 = l0[ci];
+        if (L0 < (REAL)1e-12f) L0 = (REAL)1e-12f;
+        if (dist < L0 * (REAL)2.0f && dist > (REAL)1e-12f) { /* :350 */
+          for (int d = 0; d < 3; d++) {
+            REAL t = Kat * (REAL)0.5f * (dist / L0 - (REAL)1.0f) * (delta[d] / dist);
+            forces[4 * i + d] += -t;
+            forces[4 * j + d] += t;
+          }
+        }
+      }
+    }
+  }
+}
+
 /* EulerPosition :371-381 */
 void FN(oracle3d_euler)(int nc, int nv, REAL *verts, const REAL *forces, REAL dt) {
   size_t n = (size_t)nc * nv;

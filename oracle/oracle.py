@@ -114,6 +114,33 @@ def run3d(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, nsteps, dt, which=1
     return V, Fo
 
 
+def attract3d(verts4, l0, Kat, PBC, L, nc, forces=None, dtype=np.float32):
+    """AllVertAttraction (shaders/Cell3D_Kernel.cl:313-364), literal scatter form, ACCUMULATED into `forces`
+    (zeros if None).  Returns the forces array."""
+    ct, sfx = _real(dtype)
+    V = np.ascontiguousarray(verts4, dtype=dtype).reshape(-1, 4)
+    nv = V.shape[0] // nc
+    Fo = np.zeros_like(V) if forces is None else np.ascontiguousarray(forces, dtype=dtype).reshape(-1, 4)
+    l0a = _arr(l0, nc, dtype)
+    fn = getattr(lib(), "oracle3d_attract" + sfx)
+    fn.restype = None
+    fn(nc, nv, _p(V, ct), _p(Fo, ct), _p(l0a, ct), ct(L), int(PBC), ct(Kat))
+    return Fo
+
+
+def run3d_attract(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, Kat, PBC, L, nsteps, dt, which=15, dtype=np.float32):
+    """nsteps of {the six live kernels + AllVertAttraction; Euler}: the all-pairs reference algorithm with the dead
+    attraction kernel enqueued between RepellingForces and EulerPosition.  Returns (verts4, last_forces4)."""
+    nc = len(np.asarray(v0))
+    V = np.array(verts4, dtype=dtype, copy=True).reshape(-1, 4)
+    Fo = np.zeros_like(V)
+    for _ in range(int(nsteps)):
+        Fo = forces3d(V, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, which=which, dtype=dtype)
+        Fo = attract3d(V, l0, Kat, PBC, L, nc, forces=Fo, dtype=dtype)
+        V[:, :3] += Fo[:, :3] * dtype(dt)
+    return V, Fo
+
+
 def run3d_culled(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, nsteps, dt, dtype=np.float32, rebuild_every=1):
     """nsteps of the CULLED form (CPU cell list + literal kernels; equal to the all-pairs form, see the tests) — fast
     enough for 1e4-step trajectories.  The candidate lists are rebuilt from the current fp32 AABBs every

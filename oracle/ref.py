@@ -101,3 +101,18 @@ def euler2d(verts2, nv, Ka, Kl, Kb, a0, l0, r0, Kre, Kat, PBC, L, nsteps, dt):
     if rc != 0:
         raise RuntimeError("reference CLEulerUpdate failed: " + lib().ref_last_error().decode())
     return V, F, sec.value
+
+
+def attract3d(verts4, l0, Kat, PBC, L):
+    """The reference's AllVertAttraction kernel (shaders/Cell3D_Kernel.cl:313-364), unmodified text, launched on its own on
+    zeroed forces (the reference host never enqueues it).  verts4: (nc*162,4).  Returns forces4."""
+    V4 = np.asarray(verts4, np.float32).reshape(-1, 4)
+    nc = V4.shape[0] // 162
+    v3 = np.ascontiguousarray(V4[:, :3]); f3 = np.zeros_like(v3)
+    l0a = np.ascontiguousarray(np.broadcast_to(np.asarray(l0, np.float32), (nc,)))
+    rc = lib().ref3d_attract(nc, _p(v3), _p(f3), _p(l0a), C.c_float(L), int(PBC), C.c_float(Kat))
+    if rc != 0:
+        raise RuntimeError("reference AllVertAttraction failed: " + lib().ref_last_error().decode())
+    Fo = np.zeros_like(V4)
+    Fo[:, :3] = f3
+    return Fo

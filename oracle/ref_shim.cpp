@@ -113,6 +113,51 @@ int ref3d_euler(int nc, float *verts3, float *forces3, const float *Kv, const fl
   }
 }
 
+// ---- AllVertAttraction of the reference's Cell3D_Kernel.cl, run on its own -----------------------------------------
+// The reference host never enqueues this kernel (it is compiled with the program but no cl::Kernel is made for it),
+// so there is no host code of the reference to call: this entry builds the reference's UNMODIFIED kernel text with the
+// reference's build options (src/Tissue3D.cpp:199) and launches that one kernel on zeroed forces over the
+// (NV, NCELLS) range its get_global_id(0/1) indexing expects (the reference's vertCellSize, src/Tissue3D.cpp:360).
+// verts3: nc*162*3 in; forces3: nc*162*3 out.  Returns 0, or -1 with ref_last_error().
+int ref3d_attract(int nc, const float *verts3, float *forces3, const float *l0, float L, int PBC, float Kat) {
+  try {
+    cl::Device device = cl::Device::getDefault();
+    if (!device.id) { g_err = "no OpenCL device"; return -1; }
+    cl::Context context({device});
+    cl::Program program(context, std::string(ref_cl3d_src));
+    cl_int err = program.build({device}, "-cl-opt-disable -Werror");
+    if (err != CL_SUCCESS) { g_err = "build failed: " + program.getBuildInfo<CL_PROGRAM_BUILD_LOG>(device); return -1; }
+    const int NV = 162;
+    std::vector<cl_float3> V((size_t)nc * NV), F((size_t)nc * NV);
+    for (size_t i = 0; i < V.size(); i++) {
+      V[i] = cl_float3{};
+      F[i] = cl_float3{};
+      V[i].s[0] = verts3[3 * i]; V[i].s[1] = verts3[3 * i + 1]; V[i].s[2] = verts3[3 * i + 2];
+    }
+    std::vector<float> l0v(l0, l0 + nc);
+    cl::Buffer gV(context, CL_MEM_READ_WRITE | CL_MEM_COPY_HOST_PTR, sizeof(cl_float3) * V.size(), V.data(), &err);
+    if (err != CL_SUCCESS) { g_err = "verts buffer"; return -1; }
+    cl::Buffer gF(context, CL_MEM_READ_WRITE | CL_MEM_COPY_HOST_PTR, sizeof(cl_float3) * F.size(), F.data(), &err);
+    if (err != CL_SUCCESS) { g_err = "forces buffer"; return -1; }
+    cl::Buffer gl0(context, CL_MEM_READ_ONLY | CL_MEM_COPY_HOST_PTR, sizeof(float) * nc, l0v.data(), &err);
+    if (err != CL_SUCCESS) { g_err = "l0 buffer"; return -1; }
+    cl::Kernel k(program, "AllVertAttraction", &err);
+    if (err != CL_SUCCESS) { g_err = "kernel AllVertAttraction not found"; return -1; }
+    k.setArg(0, gV); k.setArg(1, gF); k.setArg(2, gl0); k.setArg(3, L); k.setArg(4, nc); k.setArg(5, PBC); k.setArg(6, Kat);
+    cl::CommandQueue queue(context, device, 0, &err);
+    if (err != CL_SUCCESS) { g_err = "queue"; return -1; }
+    err = queue.enqueueNDRangeKernel(k, cl::NullRange, cl::NDRange(NV, nc));
+    if (err != CL_SUCCESS) { g_err = "enqueue failed: " + std::to_string(err); return -1; }
+    err = queue.enqueueReadBuffer(gF, CL_TRUE, 0, sizeof(cl_float3) * F.size(), F.data());
+    if (err != CL_SUCCESS) { g_err = "read failed: " + std::to_string(err); return -1; }
+    for (size_t i = 0; i < F.size(); i++) for (int d = 0; d < 3; d++) forces3[3 * i + d] = F[i].s[d];
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 // ---- Tissue2D::CLEulerUpdate of the reference --------------------------------------------------------
 // verts2/forces2: nc*S*2 padded (S >= max nv). NOTE the reference calls exit(0) if the OpenCL build fails
 // (src/Tissue2D.cpp:143-148): call ref_available() first.

@@ -30,6 +30,30 @@ def golden3d(name, ncells, start, calA, r0, phi0, Kv, Ka, Ks, Kre, dt, steps_lis
     np.savez_compressed(os.path.join(out, name + ".npz"), **res)
 
 
+def golden3d_attract(name, ncells, start, calA, r0, phi0, Kat, squeeze, out):
+    """The reference's AllVertAttraction kernel text on its own (never enqueued by the reference host): forces on zeroed
+    input forces.  The Disperse2D() layout is contracted about its centroid by `squeeze` so that neighbouring cells have
+    vertices within 2*l0 of each other (every third cell is moved by one box length, so the minimum-image branch
+    matters); two rest lengths (cells alternate l0 and 1.3*l0) exercise the l0[ci] asymmetry."""
+    verts3, L = R.disperse3d(ncells, start, calA, r0, phi0)
+    _, faces, sc = R.cell3d(start, calA, r0)
+    V = verts3.reshape(ncells, 162, 3).astype(np.float32)
+    com = V.mean(axis=1, keepdims=True)
+    centre = com.mean(axis=0, keepdims=True)
+    V = (V - com) + centre + (com - centre) * np.float32(squeeze)
+    V[::3] += np.array([L, -L, 0.0], np.float32)  # every third cell sits one box length away: only the PBC run sees it as a neighbour
+    V0 = np.zeros((ncells * 162, 4), np.float32)
+    V0[:, :3] = V.reshape(-1, 3)
+    l0 = np.float32(np.sqrt(np.float32(4.0) * sc["a0"]) / np.sqrt(np.float32(3.0)))
+    l0c = (l0 * np.where(np.arange(ncells) % 2 == 0, 1.0, 1.3)).astype(np.float32)
+    res = dict(verts0=V0, faces=faces, L=L, l0=l0c, Kat=np.float32(Kat))
+    for pbc in (0, 1):
+        F = R.attract3d(V0, l0c, Kat, pbc, L)
+        res[f"forces_pbc{pbc}"] = F
+        print(name, "pbc", pbc, "|F|max", np.abs(F).max(), "vertices with force", int((np.abs(F[:, :3]).max(axis=1) > 0).sum()))
+    np.savez_compressed(os.path.join(out, name + ".npz"), **res)
+
+
 def golden2d(name, specs, phi0, Ka, Kl, Kb, Kre, Kat, dt, steps_list, out):
     """specs: list of (calA, nv, r0) prototypes, tiled like the reference demos."""
     cells = [R.cell2d(0.0, 0.0, *s) for s in specs]
@@ -64,5 +88,6 @@ if __name__ == "__main__":
     golden3d("ref3d_test3dpy_16", 16, [0.0, 0.0, 0.0], 1.0, 1.0, 0.35, 5.0, 2.0, 3.0, 25.0, 0.01, [1, 10], out)
     golden3d("ref3d_test3dcpp_12", 12, [7.0, 6.0, 1.3], 1.05, 1.8, 0.35, 1.0, 1.0, 1.0, 50.0, 0.005, [1, 25], out)
     # reference test2D.cpp (32 cells = BASELINE config A) and a Kat != 0 variant
+    golden3d_attract("ref3d_attract_12", 12, [0.0, 0.0, 0.0], 1.0, 1.0, 0.35, 0.7, 0.72, out)
     golden2d("ref2d_test2d_32", [(1.05, 32, 1.0)] * 32, 0.85, 1.0, 1.0, 0.1, 50.0, 0.0, 0.005, [1, 20], out)
     golden2d("ref2d_kat_24", [(1.2, 25, 1.0)] * 24, 0.9, 0.1, 1.0, 0.05, 1.0, 0.5, 0.005, [1, 20], out)

@@ -11,6 +11,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     out, nx, ny, subdiv, nsteps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+    Kat = float(sys.argv[6]) if len(sys.argv) > 6 else 0.0  # != 0: vertex-vertex attraction on (DPM3D_ATTRACT)
     import torch
     import torch.distributed as dist
 
@@ -26,8 +27,10 @@ def main():
     h = Dpm3D(d["nc"], d["nv"], d["faces"], device=local)
     h.shard_init(rank, world, uid, max_ghost=max(8, 3 * ny))
     h.set_global_ids(d["gid"])
+    if Kat != 0.0:
+        h.set_force_mask(15 | 16)
     h.upload(d["verts"], *[d[k] for k in PK])
-    h.step(nsteps, float(d["dt"]), float(d["Kre"]), 0.0, d["PBC"], float(d["L"]))
+    h.step(nsteps, float(d["dt"]), float(d["Kre"]), Kat, d["PBC"], float(d["L"]))
     V, F = h.download()
     st = h.stats()
     np.savez(os.path.join(out, f"rank{rank}.npz"), gid=d["gid"], verts=V, forces=F, rebuilds=st.rebuilds, halo_bytes=st.halo_bytes,

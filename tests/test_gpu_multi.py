@@ -23,8 +23,9 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("world,nx,ny,subdiv,nsteps", [(2, 8, 6, 2, 40), (2, 6, 4, 3, 12), (4, 12, 4, 2, 25)])
-def test_sharded_run_equals_single_gpu_bit_for_bit(world, nx, ny, subdiv, nsteps):
+@pytest.mark.parametrize("world,nx,ny,subdiv,nsteps,Kat", [(2, 8, 6, 2, 40, 0.0), (2, 6, 4, 3, 12, 0.0), (4, 12, 4, 2, 25, 0.0),
+                                                           (2, 8, 6, 2, 30, 0.5)])
+def test_sharded_run_equals_single_gpu_bit_for_bit(world, nx, ny, subdiv, nsteps, Kat):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     from opencl_dpm_b200 import Dpm3D, synth
@@ -32,14 +33,16 @@ def test_sharded_run_equals_single_gpu_bit_for_bit(world, nx, ny, subdiv, nsteps
     with tempfile.TemporaryDirectory() as out:
         port = 29500 + (os.getpid() % 2000)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-               "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), out, str(nx), str(ny), str(subdiv), str(nsteps)]
+               "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), out, str(nx), str(ny), str(subdiv), str(nsteps), str(Kat)]
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
         d = synth.monolayer3d(nx, ny, subdiv=subdiv)
         PK = ("Kv", "Ka", "Ks", "v0", "a0", "l0")
         h = Dpm3D(d["nc"], d["nv"], d["faces"])
+        if Kat != 0.0:  # vertex-vertex attraction (gather form: ghosts stay read-only, no reverse exchange)
+            h.set_force_mask(15 | 16)
         h.upload(d["verts"], *[d[k] for k in PK])
-        h.step(nsteps, float(d["dt"]), float(d["Kre"]), 0.0, d["PBC"], float(d["L"]))
+        h.step(nsteps, float(d["dt"]), float(d["Kre"]), Kat, d["PBC"], float(d["L"]))
         V1, F1 = h.download()
         V1 = V1.reshape(d["nc"], d["nv"], 4)
         F1 = F1.reshape(d["nc"], d["nv"], 4)
