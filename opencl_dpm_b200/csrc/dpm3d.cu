@@ -455,9 +455,11 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
     p.flag_in = h->flag[h->cur]; p.flag_out = h->flag[h->cur ^ 1];
     p.force_out = (s == nsteps - 1) ? h->force : nullptr;  // forces are only read back after the last step (:425-434)
     if (repel || attract) {
-      DPM_CUDA_TRY(launch_pdl(dpm3d_units_kernel, h->nc, UNITS_THREADS, 0, h->stream, p));
+      DPM_CUDA_TRY(attract ? launch_pdl(dpm3d_units_kernel<true>, h->nc, UNITS_THREADS, 0, h->stream, p)
+                           : launch_pdl(dpm3d_units_kernel<false>, h->nc, UNITS_THREADS, 0, h->stream, p));
       if (tr) cudaEventRecord(tev[2], h->stream);
-      DPM_CUDA_TRY(launch_pdl(dpm3d_contact_kernel, h->contact_grid, CONTACT_THREADS, 0, h->stream, p));
+      DPM_CUDA_TRY(attract ? launch_pdl(dpm3d_contact_kernel<true>, h->contact_grid, CONTACT_THREADS, 0, h->stream, p)
+                           : launch_pdl(dpm3d_contact_kernel<false>, h->contact_grid, CONTACT_THREADS, 0, h->stream, p));
     } else if (tr) cudaEventRecord(tev[2], h->stream);
     if (tr) cudaEventRecord(tev[3], h->stream);
     DPM_CUDA_TRY(launch_step(h, p));

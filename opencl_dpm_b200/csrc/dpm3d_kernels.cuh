@@ -368,7 +368,9 @@ constexpr int UNITS_THREADS = 256;
 constexpr int UNITS_VPT = 4;  // nv <= 1024
 constexpr int UNITS_KMAX = 128;
 
-static __global__ void __launch_bounds__(UNITS_THREADS, 4) dpm3d_units_kernel(Step3DParams P) {
+// ATT: DPM3D_ATTRACT is selected (the default instantiation carries none of the attraction code)
+template <bool ATT>
+__global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams P) {
   __shared__ float4 sLo[UNITS_KMAX], sHi[UNITS_KMAX], sSph[UNITS_KMAX];
   __shared__ int sCand[UNITS_KMAX];
   __shared__ int sWarp[UNITS_THREADS / 32];
@@ -378,7 +380,7 @@ static __global__ void __launch_bounds__(UNITS_THREADS, 4) dpm3d_units_kernel(St
   griddep_launch();
   // state of the previous timestep's step kernel (complete before the kernel ahead of this one started): read it now
   const float4 bi0 = P.bnd_in[BND * (size_t)ci], bi1 = P.bnd_in[BND * (size_t)ci + 1], bi2 = P.bnd_in[BND * (size_t)ci + 2];
-  const bool att = (P.mask & DPM3D_ATTRACT) != 0;
+  constexpr bool att = ATT;
   const float l0i = att ? P.bnd_in[BND * (size_t)ci + 3].w : 0.0f;
   float4 myp[UNITS_VPT];
 #pragma unroll
@@ -506,7 +508,8 @@ static __global__ void __launch_bounds__(UNITS_THREADS, 4) dpm3d_units_kernel(St
 // ---------------------------------------------------------------------------------
 constexpr int CONTACT_THREADS = 256;
 
-static __global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(Step3DParams P) {
+template <bool ATT>
+__global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(Step3DParams P) {
   const int lane = threadIdx.x & 31;
   const int g = lane & (UNIT_LANES - 1);
   const int gshift = lane & ~(UNIT_LANES - 1);
@@ -527,7 +530,7 @@ static __global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(S
     const float4 p = P.pos_in[rec.x];
     const float4 bi2 = P.bnd_in[BND * (size_t)ci + 2];
     const float4 bj1 = P.bnd_in[BND * (size_t)cj + 1], bj2 = P.bnd_in[BND * (size_t)cj + 2], bj3 = P.bnd_in[BND * (size_t)cj + 3];
-    const bool att = (P.mask & DPM3D_ATTRACT) != 0;
+    constexpr bool att = ATT;
     float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
     if (P.pbc) {  // shift = L * round((COMi - COMJ) / L)   (:277-281)
       sh.x = P.L * roundf((bi2.x - bj2.x) / P.L);

@@ -6,12 +6,21 @@
 #include <pybind11/stl.h>
 
 #include "Tissue.hpp"
+#include "disperse.hpp"
 
 namespace py = pybind11;
 using namespace DPM;
 
 PYBIND11_MODULE(clDPM, m) {
   m.doc() = "Deformable Particle Model — B200-native (CUDA sm_100a) drop-in for OpenCL_DPM's clDPM";
+
+  // test hook (not part of the reference surface): the centre relaxation behind Disperse()/Disperse2D(), in its binned
+  // form (what the classes use) or in the reference's all-pairs form; returns (X, Y, hit_iteration_cap)
+  m.def("_relax_centres", [](const std::vector<float> &radius, float L, bool allpairs) {
+    std::vector<float> X, Y;
+    const bool cap = allpairs ? DPM::detail::relax_centres_allpairs(radius, L, X, Y) : DPM::detail::relax_centres(radius, L, X, Y);
+    return py::make_tuple(X, Y, cap);
+  });
 
   py::class_<Cell2D>(m, "Cell2D")
       .def(py::init<float, float, float, unsigned int, float>())

@@ -1,7 +1,7 @@
 """Generates the golden vectors in tests/golden/*.npz by running the REAL reference (oracle/_ref: the reference's
 own host code and OpenCL kernels on NVIDIA's OpenCL) — run on the GPU box:
 
-    gpurun -- 'python tests/golden/make_golden.py gpurun_out/golden'
+    gpurun -- 'python tests/golden/make_golden.py gpurun_out/golden [attract]'
 
 and copy gpurun_out/golden/*.npz into tests/golden/.  Inputs are the reference's demo configurations, built with
 the reference's own constructors and Disperse()/Disperse2D() (unseeded drand48 re-armed to its initial state).
@@ -84,6 +84,10 @@ if __name__ == "__main__":
     if not R.available():
         raise SystemExit("no OpenCL device: run this on the GPU box")
     print("reference device:", R.device_name())
+    only = sys.argv[2] if len(sys.argv) > 2 else ""  # optional: regenerate one fixture family ("attract")
+    if only == "attract":
+        golden3d_attract("ref3d_attract_12", 12, [0.0, 0.0, 0.0], 1.0, 1.0, 0.35, 0.7, 0.72, out)
+        raise SystemExit(0)
     # reference test3D.py (16 cells to keep the fixture small) and test3D.cpp's cell type
     golden3d("ref3d_test3dpy_16", 16, [0.0, 0.0, 0.0], 1.0, 1.0, 0.35, 5.0, 2.0, 3.0, 25.0, 0.01, [1, 10], out)
     golden3d("ref3d_test3dcpp_12", 12, [7.0, 6.0, 1.3], 1.05, 1.8, 0.35, 1.0, 1.0, 1.0, 50.0, 0.005, [1, 25], out)

@@ -142,3 +142,28 @@ def test_disperse_bit_exact_vs_reference():
     T2.Disperse()
     mine2 = np.stack([np.asarray(x.Verts, np.float32) for x in T2.Cells])
     assert np.float32(T2.L) == Lr2 and np.array_equal(mine2, vr2)
+
+
+@needs_ref
+def test_binned_disperse_bit_exact_vs_reference_on_larger_tissues():
+    """The host classes relax the cell centres over Verlet lists on a bin grid (opencl_dpm_b200/host/disperse.hpp, active
+    from 64 cells) instead of the reference's all-pairs loop.  The REAL reference (oracle/_ref) on
+    tissues large enough for the binned path: positions must still be equal bit for bit, i.e. same iteration count, same
+    summation order."""
+    import helpers as H
+
+    m = H.cldpm()
+    vr, Lr = R.disperse3d(96, [0.0, 0.0, 0.0], 1.0, 1.0, 0.35)
+    c = m.Cell3D([0.0, 0.0, 0.0], 1.0, 1.0)
+    T = m.Tissue3D([c] * 96, 0.35)
+    H.reset_drand48()
+    T.Disperse2D()
+    mine = np.concatenate([np.asarray(x.Verts, np.float32) for x in T.Cells])
+    assert np.float32(T.L) == Lr and np.array_equal(mine, vr)
+    vr2, Lr2 = R.disperse2d(150, 1.05, 16, 1.0, 0.85)
+    c2 = m.Cell2D(0.0, 0.0, 1.05, 16, 1.0)
+    T2 = m.Tissue2D([c2] * 150, 0.85)
+    H.reset_drand48()
+    T2.Disperse()
+    mine2 = np.stack([np.asarray(x.Verts, np.float32) for x in T2.Cells])
+    assert np.float32(T2.L) == Lr2 and np.array_equal(mine2, vr2)

@@ -143,3 +143,47 @@ def test_disperse_separates_cells_and_keeps_shapes():
     z0 = np.asarray(T3.Cells[0].Verts)[:, 2].copy()
     T3.Disperse2D()
     assert np.array_equal(np.asarray(T3.Cells[0].Verts)[:, 2], z0)  # z untouched (src/Tissue3D.cpp:106-115)
+
+
+def test_binned_centre_relaxation_equals_all_pairs_bit_for_bit():
+    """Disperse()/Disperse2D(): Verlet lists over a bin grid vs the reference's all-pairs loop restated next to it
+    (disperse.hpp) — mixed radii, sizes beyond what the real reference finishes quickly; identical floats and the same
+    stopping iteration.  (tests/test_golden_cpu.py checks the binned form against the real reference on smaller tissues.)"""
+    import time
+
+    import helpers as H
+
+    m = H.cldpm()
+    for n, r, phi in ((100, 1.0, 0.85), (500, 1.0, 0.85), (300, 2.0, 0.5)):
+        L = float(np.sqrt(n * np.pi * r * r) / phi)
+        rad = [r if i % 2 == 0 else 1.3 * r for i in range(n)]
+        H.reset_drand48()
+        t0 = time.time()
+        Xa, Ya, capa = m._relax_centres(rad, L, False)
+        ta = time.time() - t0
+        H.reset_drand48()
+        t0 = time.time()
+        Xb, Yb, capb = m._relax_centres(rad, L, True)
+        tb = time.time() - t0
+        assert capa == capb
+        assert np.array_equal(np.asarray(Xa, np.float32), np.asarray(Xb, np.float32))
+        assert np.array_equal(np.asarray(Ya, np.float32), np.asarray(Yb, np.float32))
+        print(f"n={n}: binned {ta:.2f} s, all-pairs {tb:.2f} s")
+
+
+def test_disperse_4096_cells_finishes():
+    """BASELINE config B/D sizes were out of reach of the reference's own initialiser (O(N^2) x up to 1e5 iterations)."""
+    import time
+
+    import helpers as H
+
+    m = H.cldpm()
+    c = m.Cell2D(0.0, 0.0, 1.2, 16, 1.0)
+    T = m.Tissue2D([c] * 4096, 0.85)
+    H.reset_drand48()
+    t0 = time.time()
+    T.Disperse()
+    dt = time.time() - t0
+    X = np.array([np.asarray(x.Verts, np.float32).mean(0) for x in T.Cells])
+    assert np.isfinite(X).all() and dt < 120
+    print(f"Disperse of 4096 cells: {dt:.1f} s")
