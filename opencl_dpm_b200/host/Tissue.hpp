@@ -29,6 +29,8 @@ public:
 
   void CLEulerUpdate(int nsteps, float dt);
   void Disperse2D();
+  // extension: append the current vertex positions to a flat binary trajectory (host/trajectory.cpp)
+  void AppendFrame(const std::string &path);
 
 private:
   std::shared_ptr<DeviceHandle3D> dev;  // created on first use; copies of a Tissue share it
@@ -46,6 +48,7 @@ public:
   Tissue2D(std::vector<DPM::Cell2D> cells, float phi0);
   void Disperse();
   void CLEulerUpdate(int nsteps, float dt);
+  void AppendFrame(const std::string &path);  // extension, see Tissue3D::AppendFrame
 
 private:
   int maxNV;

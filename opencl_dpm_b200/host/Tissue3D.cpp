@@ -54,7 +54,7 @@ void Tissue3D::Disperse2D() {
   // reference :106-115 — the centre is SUBTRACTED (sic), z is left untouched
   for (int i = 0; i < NCELLS; i++) {
     std::array<float, 3> com = Cells[i].GetCOM();
-    for (unsigned int j = 0; j < Cells[i].NV; j++) {
+    for (unsigned int j = 0; j < Cells[i].nverts(); j++) {
       Cells[i].Verts[j][0] -= com[0];
       Cells[i].Verts[j][1] -= com[1];
       Cells[i].Verts[j][0] -= X[i];
@@ -64,8 +64,9 @@ void Tissue3D::Disperse2D() {
 }
 
 void Tissue3D::CLEulerUpdate(int nsteps, float dt) {
-  const int NF = Cell3D::NF;
-  const int NV = Cell3D::NV;
+  // the reference hard-codes Cell3D::NF / Cell3D::NV (:119-120); cells built with a subdivision level carry their own
+  const int NF = NCELLS > 0 && !Cells.empty() ? (int)Cells[0].nfaces() : (int)Cell3D::NF;
+  const int NV = NCELLS > 0 && !Cells.empty() ? (int)Cells[0].nverts() : (int)Cell3D::NV;
 
   // ---- argument validation: same conditions, messages and exception types as reference :123-135
   if (nsteps <= 0) {
@@ -96,6 +97,11 @@ void Tissue3D::CLEulerUpdate(int nsteps, float dt) {
   std::vector<float> Kv(NCELLS), Ka(NCELLS), Ks(NCELLS), v0(NCELLS), a0(NCELLS), l0(NCELLS);
   for (int ci = 0; ci < NCELLS; ci++) {
     const Cell3D &c = Cells[ci];
+    if ((int)c.nverts() != NV || (int)c.nfaces() != NF || (int)c.Forces.size() != NV) {
+      // one topology for the whole tissue, as in the reference (Cells[0].Faces is the only face list it uploads)
+      std::cerr << "[ERROR] Cell " << ci << " has " << c.nverts() << " vertices, cell 0 has " << NV << std::endl;
+      throw std::runtime_error("All cells of a tissue must share one mesh");
+    }
     if (c.Kv <= 0 || c.Ka <= 0 || c.Ks <= 0) {
       std::cerr << "[ERROR] Invalid spring constants for cell " << ci << ": Kv=" << c.Kv << ", Ka=" << c.Ka
                 << ", Ks=" << c.Ks << std::endl;

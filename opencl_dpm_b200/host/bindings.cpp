@@ -39,19 +39,25 @@ PYBIND11_MODULE(clDPM, m) {
       .def_readwrite("Kre", &Tissue2D::Kre)
       .def_readwrite("Kat", &Tissue2D::Kat)
       .def("CLEulerUpdate", &Tissue2D::CLEulerUpdate)
+      .def("AppendFrame", &Tissue2D::AppendFrame)
       .def("Disperse", &Tissue2D::Disperse);
 
   py::class_<Cell3D>(m, "Cell3D")
       .def(py::init<std::array<float, 3>, float, float>())
+      // extension: Cell3D(start, calA, r0, subdivisions) — 3 gives the 642-vertex mesh of BASELINE configs D/E
+      .def(py::init<std::array<float, 3>, float, float, int>())
+      .def_readonly("subdivisions", &Cell3D::subdivisions)
+      .def_property_readonly("NV", &Cell3D::nverts)
+      .def_property_readonly("NF", &Cell3D::nfaces)
       .def_readwrite("Kv", &Cell3D::Kv)
       .def_readwrite("Ka", &Cell3D::Ka)
       .def_readwrite("Ks", &Cell3D::Ks)
       .def_readwrite("Verts", &Cell3D::Verts)
       .def("GetVolume", &Cell3D::GetVolume)
-      .def("GetPositions", &Cell3D::GetPositions)
-      .def("GetVesselPositions", &Cell3D::GetVesselPositions)
-      .def("GetFaces", &Cell3D::GetFaces)
-      .def("GetForces", &Cell3D::GetForces);
+      .def("GetPositions", &Cell3D::GetPositionsV)
+      .def("GetVesselPositions", &Cell3D::GetVesselPositionsV)
+      .def("GetFaces", &Cell3D::GetFacesV)
+      .def("GetForces", &Cell3D::GetForcesV);
 
   py::class_<Tissue3D>(m, "Tissue3D")
       .def(py::init<std::vector<Cell3D>, float>())
@@ -64,5 +70,6 @@ PYBIND11_MODULE(clDPM, m) {
       .def_readonly("L", &Tissue3D::L)
       .def_readonly("PBC", &Tissue3D::PBC)
       .def("CLEulerUpdate", &Tissue3D::CLEulerUpdate)
+      .def("AppendFrame", &Tissue3D::AppendFrame)
       .def("Disperse2D", &Tissue3D::Disperse2D);
 }

@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <stdexcept>
+#include <string>
 
 #include "dpm_b200.h"
 
@@ -54,22 +55,27 @@ float Cell2D::GetPerim() {
 
 // ---- 3D ---------------------------------------------------------------------------
 // reference src/cell.cpp:62-158
-Cell3D::Cell3D(std::array<float, 3> start, float calA, float radius) {
+Cell3D::Cell3D(std::array<float, 3> start, float calA, float radius) : Cell3D(start, calA, radius, 2) {}
+
+Cell3D::Cell3D(std::array<float, 3> start, float calA, float radius, int subdiv) {
+  if (subdiv < 0 || subdiv > 3) throw std::invalid_argument("Cell3D: subdivisions must be 0..3 (12, 42, 162 or 642 vertices)");
+  subdivisions = subdiv;
   calA0 = calA;
   r0 = radius;
   Kv = 0.0f;
   Ka = 0.0f;
   Ks = 0.0f;  // uninitialised in the reference
-  std::vector<float> unit(3 * NV);
-  std::vector<uint32_t> tri(3 * NF);
-  int nv = 0, nf = 0;
-  if (dpm_icosphere(2, unit.data(), tri.data(), &nv, &nf) != DPM_OK || nv != (int)NV || nf != (int)NF)
+  const unsigned int nf = 20u << (2 * subdiv), nv = nf / 2 + 2;  // 4^s * 20 faces; Euler: V = F/2 + 2
+  std::vector<float> unit(3 * nv);
+  std::vector<uint32_t> tri(3 * nf);
+  int gv = 0, gf = 0;
+  if (dpm_icosphere(subdiv, unit.data(), tri.data(), &gv, &gf) != DPM_OK || gv != (int)nv || gf != (int)nf)
     throw std::runtime_error("icosphere construction failed");
-  Verts.resize(NV);
-  Forces.assign(NV, {0.0f, 0.0f, 0.0f});
-  Faces.resize(NF);
-  for (unsigned int f = 0; f < NF; f++) Faces[f] = {tri[3 * f], tri[3 * f + 1], tri[3 * f + 2]};
-  for (unsigned int v = 0; v < NV; v++)
+  Verts.resize(nv);
+  Forces.assign(nv, {0.0f, 0.0f, 0.0f});
+  Faces.resize(nf);
+  for (unsigned int f = 0; f < nf; f++) Faces[f] = {tri[3 * f], tri[3 * f + 1], tri[3 * f + 2]};
+  for (unsigned int v = 0; v < nv; v++)
     for (int d = 0; d < 3; d++) {
       float x = unit[3 * v + d];
       x *= r0;
@@ -78,7 +84,7 @@ Cell3D::Cell3D(std::array<float, 3> start, float calA, float radius) {
     }
   v0 = (4.0f / 3.0f) * M_PI * pow(r0, 3);
   sa0 = pow((6 * sqrt(M_PI) * v0 * calA), (2.0f / 3.0f));
-  a0 = (sa0 / (float)NF);
+  a0 = (sa0 / (float)nf);
   Volume = GetVolume();
   SurfaceArea = GetSurfaceArea();
 }
@@ -112,7 +118,13 @@ float Cell3D::GetSurfaceArea() {
   return area;
 }
 
+static void need_reference_mesh(const Cell3D &c, const char *what) {
+  if (c.nverts() != Cell3D::NV || c.nfaces() != Cell3D::NF)
+    throw std::logic_error(std::string(what) + ": fixed-size result needs the 162-vertex mesh; use the ...V() form");
+}
+
 std::array<std::array<float, Cell3D::NV>, 3> Cell3D::GetPositions() {
+  need_reference_mesh(*this, "GetPositions");
   std::array<std::array<float, NV>, 3> out;
   for (unsigned int v = 0; v < NV; v++)
     for (int d = 0; d < 3; d++) out[d][v] = Verts[v][d];
@@ -121,10 +133,42 @@ std::array<std::array<float, Cell3D::NV>, 3> Cell3D::GetPositions() {
 
 // wraps the monolayer around a cylinder of circumference L (src/cell.cpp:242-253)
 std::array<std::array<float, 162>, 3> Cell3D::GetVesselPositions(float L) {
+  need_reference_mesh(*this, "GetVesselPositions");
   std::array<std::array<float, NV>, 3> out;
+  const std::vector<std::vector<float>> v = GetVesselPositionsV(L);
+  for (int d = 0; d < 3; d++)
+    for (unsigned int i = 0; i < NV; i++) out[d][i] = v[d][i];
+  return out;
+}
+
+std::array<std::array<float, Cell3D::NV>, 3> Cell3D::GetForces() {
+  need_reference_mesh(*this, "GetForces");
+  std::array<std::array<float, NV>, 3> out;
+  for (unsigned int v = 0; v < NV; v++)
+    for (int d = 0; d < 3; d++) out[d][v] = Forces[v][d];
+  return out;
+}
+
+std::array<std::array<int, 3>, Cell3D::NF> Cell3D::GetFaces() {
+  need_reference_mesh(*this, "GetFaces");
+  std::array<std::array<int, 3>, NF> out;
+  for (unsigned int f = 0; f < NF; f++)
+    for (int k = 0; k < 3; k++) out[f][k] = (int)Faces[f][k];
+  return out;
+}
+
+std::vector<std::vector<float>> Cell3D::GetPositionsV() {
+  std::vector<std::vector<float>> out(3, std::vector<float>(nverts()));
+  for (unsigned int v = 0; v < nverts(); v++)
+    for (int d = 0; d < 3; d++) out[d][v] = Verts[v][d];
+  return out;
+}
+
+std::vector<std::vector<float>> Cell3D::GetVesselPositionsV(float L) {
+  std::vector<std::vector<float>> out(3, std::vector<float>(nverts()));
   const float scale = (2.0 * M_PI) / L;
   const float radius = L / (2 * M_PI);
-  for (unsigned int v = 0; v < NV; v++) {
+  for (unsigned int v = 0; v < nverts(); v++) {
     const float theta = Verts[v][0] * scale;
     out[0][v] = (radius - Verts[v][2]) * cos(theta);
     out[2][v] = (radius - Verts[v][2]) * sin(theta);
@@ -133,25 +177,26 @@ std::array<std::array<float, 162>, 3> Cell3D::GetVesselPositions(float L) {
   return out;
 }
 
-std::array<std::array<float, Cell3D::NV>, 3> Cell3D::GetForces() {
-  std::array<std::array<float, NV>, 3> out;
-  for (unsigned int v = 0; v < NV; v++)
+std::vector<std::vector<float>> Cell3D::GetForcesV() {
+  std::vector<std::vector<float>> out(3, std::vector<float>(nverts()));
+  for (unsigned int v = 0; v < nverts(); v++)
     for (int d = 0; d < 3; d++) out[d][v] = Forces[v][d];
   return out;
 }
 
-std::array<std::array<int, 3>, Cell3D::NF> Cell3D::GetFaces() {
-  std::array<std::array<int, 3>, NF> out;
-  for (unsigned int f = 0; f < NF; f++)
+std::vector<std::array<int, 3>> Cell3D::GetFacesV() {
+  std::vector<std::array<int, 3>> out(nfaces());
+  for (unsigned int f = 0; f < nfaces(); f++)
     for (int k = 0; k < 3; k++) out[f][k] = (int)Faces[f][k];
   return out;
 }
 
 std::array<float, 3> Cell3D::GetCOM() {
   std::array<float, 3> com = {0.0, 0.0, 0.0};
-  for (unsigned int v = 0; v < NV; v++)
+  const unsigned int n = nverts();
+  for (unsigned int v = 0; v < n; v++)
     for (int d = 0; d < 3; d++) com[d] += Verts[v][d];
-  for (int d = 0; d < 3; d++) com[d] /= (float)NV;
+  for (int d = 0; d < 3; d++) com[d] /= (float)n;
   return com;
 }
 

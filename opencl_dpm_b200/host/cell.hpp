@@ -27,8 +27,14 @@ struct Cell2D {
 
 class Cell3D {
 public:
-  static const unsigned int NV = 162;  // icosphere, 2 subdivisions (reference include/cell.hpp:30-31)
+  static const unsigned int NV = 162;  // icosphere, 2 subdivisions (reference include/cell.hpp:30-31): the DEFAULT mesh
   static const unsigned int NF = 320;
+  // Extension: the reference hard-codes two subdivisions; BASELINE's 642-vertex configurations need
+  // three.  A cell built with the 4-argument constructor carries its own mesh size; everything that loops over a cell
+  // uses nverts()/nfaces() (== NV/NF for the reference mesh).  0 <= subdivisions <= 3 (12, 42, 162, 642 vertices).
+  int subdivisions = 2;
+  unsigned int nverts() const { return (unsigned int)Verts.size(); }
+  unsigned int nfaces() const { return (unsigned int)Faces.size(); }
   float calA0;
   float r0;
   float v0;
@@ -51,6 +57,13 @@ public:
   std::array<std::array<int, 3>, NF> GetFaces();
   std::array<float, 3> GetCOM();
   Cell3D(std::array<float, 3> starting_point, float CalA0, float r0);
+  Cell3D(std::array<float, 3> starting_point, float CalA0, float r0, int subdivisions);
+  // size-agnostic forms of the four getters above (the fixed-size ones throw std::logic_error for a non-reference mesh);
+  // the Python module binds GetPositions/GetVesselPositions/GetForces/GetFaces to these: same list-of-lists result
+  std::vector<std::vector<float>> GetPositionsV();
+  std::vector<std::vector<float>> GetVesselPositionsV(float L);
+  std::vector<std::vector<float>> GetForcesV();
+  std::vector<std::array<int, 3>> GetFacesV();
 };
 
 }  // namespace DPM

@@ -253,3 +253,32 @@ def test_vertex_exactly_on_a_neighbour_vertex():
     assert np.isfinite(F).all() and np.isfinite(Fref).all()
     H.assert_forces_close(F, Fref, Fref64, what="repulsion with a coincident vertex")
     h.close()
+
+
+def test_cldpm_tissue3d_with_642_vertex_cells():
+    """Extension: the subdivision level through the drop-in classes.  9 cells of the 642-vertex mesh
+    (Cell3D(start, calA, r0, 3)) through Tissue3D.CLEulerUpdate vs the all-pairs oracle on the same flat arrays."""
+    O = _oracle()
+    m = H.cldpm()
+    c = m.Cell3D([0.0, 0.0, 1.0], 1.0, 1.0, 3)
+    c.Ka, c.Kv, c.Ks = 2.0, 5.0, 3.0
+    T = m.Tissue3D([c] * 9, 0.6)
+    T.Kre = 25.0
+    H.reset_drand48()
+    T.Disperse2D()
+    cells = T.Cells
+    nv = cells[0].NV
+    assert nv == 642 and cells[0].NF == 1280
+    V0 = np.zeros((9 * nv, 4), np.float32)
+    for i, x in enumerate(cells):
+        V0[i * nv:(i + 1) * nv, :3] = np.asarray(x.Verts, np.float32)
+    faces = np.asarray(cells[0].GetFaces(), np.uint32)
+    P = H.params3d(9, 1.0, 1.0, 5.0, 2.0, 3.0, nf=1280)
+    T.CLEulerUpdate(3, 0.01)
+    out = T.Cells
+    V = np.concatenate([np.asarray(x.Verts, np.float32) for x in out])
+    F = np.concatenate([np.asarray(x.GetForces(), np.float32).T for x in out])
+    Vr, Fr = O.run3d(V0, faces, *[P[k] for k in PKEYS], 25.0, int(T.PBC), np.float32(T.L), 3, np.float32(0.01))
+    assert np.abs(Fr).max() > 1.0
+    assert np.abs(V - Vr[:, :3]).max() <= 4e-6
+    assert np.abs(F - Fr[:, :3]).max() <= 4 * H.force_tol(Fr)

@@ -187,3 +187,70 @@ def test_disperse_4096_cells_finishes():
     X = np.array([np.asarray(x.Verts, np.float32).mean(0) for x in T.Cells])
     assert np.isfinite(X).all() and dt < 120
     print(f"Disperse of 4096 cells: {dt:.1f} s")
+
+
+def test_cell3d_subdivision_levels():
+    """Extension: Cell3D(start, calA, r0, subdivisions).  Level 2 is the reference mesh and the
+    3-argument constructor; level 3 is the 642-vertex mesh of BASELINE configs D/E; sizes follow V = F/2 + 2."""
+    import helpers as H
+    from opencl_dpm_b200 import capi
+
+    m = H.cldpm()
+    ref = m.Cell3D([1.0, 2.0, 3.0], 1.05, 1.8)
+    same = m.Cell3D([1.0, 2.0, 3.0], 1.05, 1.8, 2)
+    assert ref.NV == 162 and ref.NF == 320 and ref.subdivisions == 2
+    assert np.array_equal(np.asarray(ref.Verts, np.float32), np.asarray(same.Verts, np.float32)) and ref.GetFaces() == same.GetFaces()
+    for s, nv, nf in ((0, 12, 20), (1, 42, 80), (3, 642, 1280)):
+        c = m.Cell3D([0.0, 0.0, 1.0], 1.0, 1.0, s)
+        assert (c.NV, c.NF) == (nv, nf)
+        P = c.GetPositions()
+        assert len(P) == 3 and len(P[0]) == nv and len(c.GetFaces()) == nf and len(c.GetForces()[0]) == nv
+        u, f = capi.icosphere(s)
+        assert np.array_equal(np.asarray(c.Verts, np.float32), (u + np.array([0, 0, 1], np.float32)).astype(np.float32))
+        assert np.array_equal(np.asarray(c.GetFaces()), f)
+        assert 0.6 * 4.18879 < c.GetVolume() <= 4.18879 + 1e-3  # inscribed polyhedron of the unit sphere
+    with pytest.raises(ValueError):
+        m.Cell3D([0.0, 0.0, 0.0], 1.0, 1.0, 4)
+
+
+def test_tissue3d_rejects_mixed_meshes():
+    import helpers as H
+
+    m = H.cldpm()
+    a, b = m.Cell3D([0.0, 0.0, 0.0], 1.0, 1.0, 2), m.Cell3D([0.0, 0.0, 0.0], 1.0, 1.0, 3)
+    for c in (a, b):
+        c.Kv, c.Ka, c.Ks = 1.0, 1.0, 1.0
+    T = m.Tissue3D([a, b], 0.35)
+    T.Kre = 1.0
+    with pytest.raises(RuntimeError, match="share one mesh"):
+        T.CLEulerUpdate(1, 0.01)
+
+
+def test_trajectory_writer_roundtrip(tmp_path):
+    """AppendFrame (host/trajectory.cpp) + opencl_dpm_b200.traj.read: the flat binary replacement of the reference's
+    PNG-per-frame loop."""
+    import helpers as H
+    from opencl_dpm_b200 import traj
+
+    m = H.cldpm()
+    p3 = str(tmp_path / "t3.dpmt")
+    c = m.Cell3D([0.0, 0.0, 1.0], 1.0, 1.0, 3)
+    T = m.Tissue3D([c] * 5, 0.35)
+    H.reset_drand48()
+    T.AppendFrame(p3)
+    T.Disperse2D()
+    T.AppendFrame(p3)
+    r = traj.read(p3)
+    assert r["frames"].shape == (2, 5, 642, 3) and r["dim"] == 3 and r["PBC"] == 1 and abs(r["L"] - T.L) < 1e-6
+    assert np.array_equal(r["faces"], np.asarray(T.Cells[0].GetFaces()))
+    assert np.array_equal(r["frames"][1, 3], np.asarray(T.Cells[3].Verts, np.float32))
+    assert np.array_equal(r["frames"][0, 3], np.asarray(c.Verts, np.float32))
+    p2 = str(tmp_path / "t2.dpmt")
+    a, b = m.Cell2D(0.0, 0.0, 1.2, 25, 1.0), m.Cell2D(1.0, 1.0, 1.2, 22, 1.3)
+    T2 = m.Tissue2D([a, b] * 3, 0.9)
+    T2.AppendFrame(p2)
+    r2 = traj.read(p2, mmap=False)
+    assert r2["frames"].shape == (1, 6, 25, 2) and list(r2["NV"]) == [25, 22] * 3
+    assert np.array_equal(r2["frames"][0, 1, :22], np.asarray(T2.Cells[1].Verts, np.float32)) and not r2["frames"][0, 1, 22:].any()
+    with pytest.raises(RuntimeError):
+        T.AppendFrame(p2)  # a 3D tissue into a 2D file
