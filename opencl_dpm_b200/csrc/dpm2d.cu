@@ -88,6 +88,9 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
   float2 *sN = sV + S;
   float2 *sF = sN + S;
   unsigned char *sFound = reinterpret_cast<unsigned char *>(reinterpret_cast<float2 *>(smem_raw) + (size_t)W2D * 3 * S) + (size_t)warp * S;
+  // the candidate's vertices near this cell (attraction), ascending; after the found flags, 2-byte aligned
+  unsigned short *sNear = reinterpret_cast<unsigned short *>(reinterpret_cast<unsigned char *>(reinterpret_cast<float2 *>(smem_raw) + (size_t)W2D * 3 * S) +
+                                                             (((size_t)W2D * S + 1) & ~(size_t)1)) + (size_t)warp * S;
   const int n = P.nv[ci];
   const float4 cA = P.cellA[ci], cB = P.cellB[ci];
   const float Ka = cA.x, Kl = cA.y, Kb = cA.z, a0 = cA.w, l0 = cB.x, r0 = cB.y;
@@ -150,7 +153,11 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
   const int ncand = min(P.cand_count[ci], P.K);
   const bool doAtt = (P.mask & DPM2D_ATTRACT) && (P.Kat != 0.0f);  // Kat == 0 adds exact zeros in the reference
   const bool doRep = (P.mask & DPM2D_REPEL);
-  const float halfL = 0.5f * P.L;
+  const float halfL = 0.5f * P.L, invL = 1.0f / P.L;
+  // own bounding box of the current positions (exact; written by the previous step's epilogue / the bounds kernel)
+  const float4 bi0 = P.bnd_in[3 * (size_t)ci], bi1 = P.bnd_in[3 * (size_t)ci + 1];
+  const float hxi = 0.5f * (bi1.x - bi0.x), hyi = 0.5f * (bi1.y - bi0.y), cxi = 0.5f * (bi0.x + bi1.x), cyi = 0.5f * (bi0.y + bi1.y);
+  const bool own_cull_ok = !P.pbc || ((hxi + l0 < 0.25f * P.L) && (hyi + l0 < 0.25f * P.L));
   unsigned evals = 0;
   if (doAtt || doRep) {
     for (int k = 0; k < ncand; k++) {
@@ -159,8 +166,8 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
       const float hx = 0.5f * (bj1.x - bj0.x), hy = 0.5f * (bj1.y - bj0.y);
       const float cxj = 0.5f * (bj0.x + bj1.x), cyj = 0.5f * (bj0.y + bj1.y);
       const bool att_cull_ok = !P.pbc || ((hx + l0 < 0.25f * P.L) && (hy + l0 < 0.25f * P.L));
-      int nj = 0;
-      bool staged = false;
+      int nj = 0, nnear = 0;
+      bool staged = false, nearBuilt = false;
       for (int ch = 0; ch < nchunk; ch++) {
         const int vi = lane + 32 * ch;
         const bool act = vi < n;
@@ -176,7 +183,9 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
         }
         if (act && doAtt) {
           float dx = p.x - cxj, dy = p.y - cyj;
-          if (P.pbc) { dx -= P.L * roundf(dx / P.L); dy -= P.L * roundf(dy / P.L); }
+          // cull only: the quotient by multiplication; its rounding can differ from dx / L only half a box away from the
+          // candidate, where either image is far outside l0 (att_cull_ok bounds the box size)
+          if (P.pbc) { dx -= P.L * roundf(dx * invL); dy -= P.L * roundf(dy * invL); }
           const float ax = fmaxf(fabsf(dx) - hx, 0.0f), ay = fmaxf(fabsf(dy) - hy, 0.0f);
           wantAtt = !att_cull_ok || (ax * ax + ay * ay <= l0 * l0 * 1.0001f + 1e-12f);
         }
@@ -191,44 +200,53 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
           __syncwarp();
           staged = true;
         }
-        // attraction: lanes split the neighbour's vertices; nonzero terms are folded in ascending vertex order
-        while (mAtt) {
-          const int src = __ffs(mAtt) - 1;
-          mAtt &= mAtt - 1;
-          const float px = __shfl_sync(0xffffffffu, p.x, src), py = __shfl_sync(0xffffffffu, p.y, src);
-          float fx = 0.0f, fy = 0.0f;
-          bool any = false;
-          for (int base = 0; base < nj; base += 32) {
-            const int vj = base + lane;
-            float tx = 0.0f, ty = 0.0f;
-            bool hit = false;
-            if (vj < nj) {
-              const float2 q = sN[vj];
-              float rx = q.x - px, ry = q.y - py;
+        // attraction: a neighbour vertex can only act on this cell if it lies within l0 of the cell's own bounding box
+        // (exact: dist < l0[ci] is the reference's test, :258-262), so the neighbour's ring is first compacted to those
+        // vertices, in ascending order; then every wanting vertex of the chunk (one per lane) folds the compacted list
+        // serially — ascending vj within ascending cj, the reference's summation order — out of broadcast reads.
+        if (mAtt) {
+          if (!nearBuilt) {
+            nnear = 0;
+            for (int base = 0; base < nj; base += 32) {
+              const int vj = base + lane;
+              bool near = false;
+              if (vj < nj) {
+                const float2 q = sN[vj];
+                float dx = q.x - cxi, dy = q.y - cyi;
+                if (P.pbc) { dx -= P.L * roundf(dx * invL); dy -= P.L * roundf(dy * invL); }  // cull only, see above
+                const float ax = fmaxf(fabsf(dx) - hxi, 0.0f), ay = fmaxf(fabsf(dy) - hyi, 0.0f);
+                near = !own_cull_ok || (ax * ax + ay * ay <= l0 * l0 * 1.0001f + 1e-12f);
+              }
+              const unsigned nb = __ballot_sync(0xffffffffu, near);
+              if (near) sNear[nnear + __popc(nb & ((1u << lane) - 1u))] = (unsigned short)vj;
+              nnear += __popc(nb);
+            }
+            __syncwarp();
+            nearBuilt = true;
+          }
+          if (wantAtt && nnear > 0) {
+            float2 f = sF[vi];
+            const float kn = P.Kat / (float)n;
+            const float l0sq_hi = l0 * l0 * 1.00001f;  // prefilter on the squared distance; the reference's test follows
+            for (int t = 0; t < nnear; t++) {
+              const float2 q = sN[sNear[t]];
+              float rx = q.x - p.x, ry = q.y - p.y;
               if (P.pbc) {  // rij -= L * round(rij / L)  (:254-256); a no-op unless |r| > L/2
                 if (fabsf(rx) > halfL) rx -= P.L * roundf(rx / P.L);
                 if (fabsf(ry) > halfL) ry -= P.L * roundf(ry / P.L);
               }
-              const float dist = sqrtf(rx * rx + ry * ry);
-              if (dist < l0) {
-                const float ftmp = P.Kat / (float)n * dist / l0;  // :263
-                if (dist != 0.0f) {  // OpenCL normalize(0) = 0 (two coinciding vertices; measured on the reference's runtime)
-                  tx = ftmp * (rx / dist);
-                  ty = ftmp * (ry / dist);
+              const float d2 = rx * rx + ry * ry;
+              if (d2 < l0sq_hi && d2 != 0.0f) {  // OpenCL normalize(0) = 0 (two coinciding vertices; measured on the reference's runtime)
+                const float dist = sqrtf(d2);
+                if (dist < l0) {                      // :258-262
+                  const float ftmp = kn * dist / l0;  // :263
+                  f.x += ftmp * (rx / dist);          // Forces[index] += ftmp * normalize(rij), in vj order (:264)
+                  f.y += ftmp * (ry / dist);
                 }
-                hit = true;
               }
             }
-            unsigned hm = __ballot_sync(0xffffffffu, hit);
-            while (hm) {
-              const int s2 = __ffs(hm) - 1;
-              hm &= hm - 1;
-              const float ax = __shfl_sync(0xffffffffu, tx, s2), ay = __shfl_sync(0xffffffffu, ty, s2);
-              if (!any) { const float2 f0 = sF[src + 32 * ch]; fx = f0.x; fy = f0.y; any = true; }
-              fx += ax; fy += ay;  // Forces[index] += ftmp * normalize(rij), in vj order (:264)
-            }
+            sF[vi] = f;
           }
-          if (any && lane == 0) sF[src + 32 * ch] = make_float2(fx, fy);
           __syncwarp();
         }
         // repulsion: lanes split the edges of the even-odd test; parity of all toggles
@@ -336,7 +354,7 @@ struct dpm2d_ctx {
 
 namespace {
 // per warp: own ring, staged neighbour ring, force accumulators (float2 each) + found flags (bytes)
-inline size_t smem2d_bytes(int S) { return (sizeof(float2) * 3 + 1) * (size_t)S * W2D + 16; }
+inline size_t smem2d_bytes(int S) { return (sizeof(float2) * 3 + 1 + 2) * (size_t)S * W2D + 32; }
 
 struct DeviceGuard2 {
   int prev = -1;

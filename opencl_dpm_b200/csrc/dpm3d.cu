@@ -113,20 +113,25 @@ size_t smem_for(dpm3d_ctx *h) {
 }
 
 // The step kernel variant for this mesh: ring slots read per vertex / slots every vertex has, and the compat mode.
+template <bool COMPAT, bool ATT, typename Fn>
+static cudaError_t with_step_kernel_mode(dpm3d_ctx *h, Fn &&fn) {
+  if (h->ring_stride > 8) return fn(dpm3d_step_kernel<16, 3, COMPAT, ATT>);
+  if (h->min_valence >= 5 && h->max_valence <= 6) return fn(dpm3d_step_kernel<6, 5, COMPAT, ATT>);
+  return fn(dpm3d_step_kernel<8, 3, COMPAT, ATT>);
+}
 template <typename Fn>
-static cudaError_t with_step_kernel(dpm3d_ctx *h, Fn &&fn) {
+static cudaError_t with_step_kernel(dpm3d_ctx *h, bool att, Fn &&fn) {
   const bool compat = h->stale_from >= 0;
-  if (h->ring_stride > 8) return compat ? fn(dpm3d_step_kernel<16, 3, true>) : fn(dpm3d_step_kernel<16, 3, false>);
-  if (h->min_valence >= 5 && h->max_valence <= 6) return compat ? fn(dpm3d_step_kernel<6, 5, true>) : fn(dpm3d_step_kernel<6, 5, false>);
-  return compat ? fn(dpm3d_step_kernel<8, 3, true>) : fn(dpm3d_step_kernel<8, 3, false>);
+  if (compat) return att ? with_step_kernel_mode<true, true>(h, fn) : with_step_kernel_mode<true, false>(h, fn);
+  return att ? with_step_kernel_mode<false, true>(h, fn) : with_step_kernel_mode<false, false>(h, fn);
 }
 
 cudaError_t set_smem(dpm3d_ctx *h) {
   const int smem = (int)h->smem;
-  for (int compat = 0; compat < 2; compat++) {  // both modes: dpm3d_set_compat may be called at any time
+  for (int mode = 0; mode < 4; mode++) {  // every mode: dpm3d_set_compat / the attraction may be switched at any time
     const int keep = h->stale_from;
-    h->stale_from = compat ? 0 : -1;
-    cudaError_t e = with_step_kernel(h, [&](auto *k) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    h->stale_from = (mode & 1) ? 0 : -1;
+    cudaError_t e = with_step_kernel(h, (mode & 2) != 0, [&](auto *k) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     h->stale_from = keep;
     if (e != cudaSuccess) return e;
   }
@@ -147,7 +152,7 @@ static cudaError_t launch_pdl(K *kernel, int grid, int block, size_t smem, cudaS
 }
 
 cudaError_t launch_step(dpm3d_ctx *h, const Step3DParams &p) {
-  return with_step_kernel(h, [&](auto *k) { return launch_pdl(k, p.nc, STEP_THREADS, h->smem, h->stream, p); });
+  return with_step_kernel(h, (p.mask & DPM3D_ATTRACT) != 0, [&](auto *k) { return launch_pdl(k, p.nc, STEP_THREADS, h->smem, h->stream, p); });
 }
 
 CellTopo cell_topo(dpm3d_ctx *h) {

@@ -435,20 +435,27 @@ __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams
     if (tid == 0) { P.unit_base[ci] = 0; P.unit_cnt[ci] = 0; }
     return;
   }
+  // One pass of tests: with at most 32 candidates (the default capacity) the survivors of a vertex are kept as a bit mask
+  // and the emit pass below only walks the set bits; longer lists repeat the tests when emitting.
+  const bool masked = ncand <= 32;
   int cntj[UNITS_VPT];
+  unsigned hitm[UNITS_VPT];
   int cnt = 0;
 #pragma unroll
   for (int j = 0; j < UNITS_VPT; j++) {
     const int v = tid + j * UNITS_THREADS;
     cntj[j] = 0;
+    hitm[j] = 0u;
     if (v < nv) {
       const float4 p = myp[j];
       for (int k = 0; k < ncand; k++) {
         if (sCand[k] < 0) continue;
         const float4 lo = sLo[k], hi = sHi[k], sp = sSph[k];
         const float dx = p.x - sp.x, dy = p.y - sp.y, dz = p.z - sp.z;
-        cntj[j] += (!(p.x < lo.x || p.x > hi.x || p.y < lo.y || p.y > hi.y || p.z < lo.z || p.z > hi.z) &&
-                    (dx * dx + dy * dy + dz * dz) <= sp.w) ? 1 : 0;
+        const bool in = !(p.x < lo.x || p.x > hi.x || p.y < lo.y || p.y > hi.y || p.z < lo.z || p.z > hi.z) &&
+                        (dx * dx + dy * dy + dz * dz) <= sp.w;
+        cntj[j] += in ? 1 : 0;
+        hitm[j] |= (in ? 1u : 0u) << (k & 31);
       }
       cnt += cntj[j];
     }
@@ -487,7 +494,9 @@ __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams
 #pragma unroll
   for (int j = 0; j < UNITS_VPT; j++) {
     const int v = tid + j * UNITS_THREADS;
-    if (v < nv) {
+    if (v < nv && masked) {
+      for (unsigned m = hitm[j]; m; m &= m - 1) *out++ = make_int2(ci * nv + v, sCand[__ffs(m) - 1]);  // ascending k = ascending cj
+    } else if (v < nv) {
       const float4 p = myp[j];
       for (int k = 0; k < ncand; k++) {
         const int cj = sCand[k];
@@ -643,7 +652,7 @@ struct VertPartial {  // per-thread partials over the thread's own vertices
   }
 };
 
-__device__ __forceinline__ void cell_scalars(const float4 *sP, float4 *sWide, const CellTopo &T, VertPartial vp, float vol_prev, const float4 *cellB_ci,
+__device__ __forceinline__ void cell_scalars(const float4 *sP, float4 *sWide, const CellTopo &T, VertPartial vp, float vol_prev, const float *l0_ptr,
                                              float4 *bnd_cell, unsigned char *flag_cell, const float4 *bbox_lo, const float4 *bbox_hi,
                                              NbrState *st) {
   __shared__ float sRed[STEP_WARPS][12];
@@ -744,7 +753,7 @@ __device__ __forceinline__ void cell_scalars(const float4 *sP, float4 *sWide, co
     bnd_cell[0] = make_float4(l[0], l[1], l[2], rr);
     bnd_cell[1] = make_float4(h[0], h[1], h[2], pad);
     bnd_cell[2] = make_float4(com.x, com.y, com.z, sSc[3]);
-    bnd_cell[3] = make_float4(rm, star ? 1.f : 0.f, vol_prev, cellB_ci->y);  // l0 travels with the bounds (ghost cells have no parameters)
+    bnd_cell[3] = make_float4(rm, star ? 1.f : 0.f, vol_prev, *l0_ptr);  // l0 travels with the bounds (ghost cells have no parameters)
     if (st) {  // neighbour-list validity
       const float4 bl = *bbox_lo, bh = *bbox_hi;
       if (l[0] < bl.x || l[1] < bl.y || l[2] < bl.z || h[0] > bh.x || h[1] > bh.y || h[2] > bh.z) st->rebuild = 1;
@@ -767,7 +776,7 @@ static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_bounds_kernel(const
     vp.add(p);
   }
   __syncthreads();
-  cell_scalars(sP, sWide, T, vp, 0.0f, cellB + ci, bnd + BND * (size_t)ci, flags + (size_t)ci * T.nf, nullptr, nullptr, nullptr);
+  cell_scalars(sP, sWide, T, vp, 0.0f, &cellB[ci].y, bnd + BND * (size_t)ci, flags + (size_t)ci * T.nf, nullptr, nullptr, nullptr);
 }
 
 // Walk-start table of the fast contact evaluation: for the direction of each octahedral texel, the face of cell 0 whose
@@ -874,7 +883,8 @@ __device__ __forceinline__ void ring_gather(const float4 *sP, const unsigned sho
 
 // MAXV: ring slots read per vertex (6: valence 5..6, the icospheres; 8; 16 = two 16-byte loads); MINV: ring slots
 // known to be occupied for every vertex (no bound check)
-template <int MAXV, int MINV, bool COMPAT>
+// ATT: DPM3D_ATTRACT selected with Kat != 0 (the default instantiation carries none of the attraction code)
+template <int MAXV, int MINV, bool COMPAT, bool ATT>
 __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel(Step3DParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long sBar;
@@ -909,6 +919,8 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
   const float dcoef = (COMPAT && doVol) ? (-Kv * (bi3.z / v0 - 1.0f)) * (1.0f / 6.0f) - coef : 0.0f;
   const bool doArea = (P.mask & DPM3D_AREA) && !(Ka < 1e-8f);
   const bool doStick = (P.mask & DPM3D_STICK) && !(Ks < 1e-12f);
+  __shared__ float sL0;  // handed to the epilogue through shared memory: no register held across the kernel, no global load at its end
+  if (tid == 0) sL0 = l0;
   const float inv_l0 = 1.0f / l0;
   const float scale = doArea ? Ka * sqrtf(a0) / l0 * 0.3f : 0.0f;  // :162
   const bool doRep = (P.mask & DPM3D_REPEL) && P.Kc != 0.0f;
@@ -966,7 +978,7 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
   // ---- Euler update (EulerPosition :380), outputs ----------------------------------------------------------
   // The contact weights are the only input from this timestep's units / contact kernels: everything above overlaps them.
   griddep_wait();
-  const bool doAtt = (P.mask & DPM3D_ATTRACT) && P.Kat != 0.0f;
+  constexpr bool doAtt = ATT;
   const int ucnt = (doRep || doAtt) ? P.unit_cnt[ci] : 0;
   const int ubase = (doRep || doAtt) ? P.unit_base[ci] : 0;
   const float *uw = P.unit_w + ubase;
@@ -1012,7 +1024,7 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
   // ---- next step's per-cell scalars from the NEW positions --------------------------------------------------
   CellTopo T;
   T.faces = P.faces; T.ring_nbr = P.ring_nbr; T.valence = P.valence; T.ring_stride = P.ring_stride; T.nv = nv; T.nf = nf;
-  cell_scalars(sP, sF, T, vp, bi2.w, P.cellB + ci, P.bnd_out + BND * (size_t)ci, P.flag_out + (size_t)ci * nf, P.bbox_lo + ci, P.bbox_hi + ci, P.st);
+  cell_scalars(sP, sF, T, vp, bi2.w, &sL0, P.bnd_out + BND * (size_t)ci, P.flag_out + (size_t)ci * nf, P.bbox_lo + ci, P.bbox_hi + ci, P.st);
   if (tid == 0) bulk_wait_all();  // the bulk store has read sP (and landed) before the CTA's shared memory is released
 }
 

@@ -31,6 +31,15 @@ public:
   void Disperse2D();
   // extension: append the current vertex positions to a flat binary trajectory (host/trajectory.cpp)
   void AppendFrame(const std::string &path);
+  // extension: device-resident stepping.  CLEulerUpdate must re-upload Cells and read everything back
+  // on every call because callers may edit Cells between calls (SURVEY §8b "Ownership"); a loop of many short calls pays
+  // pack + H2D + D2H + unpack each time.  StepResident uploads Cells only when the device copy is stale (first use, after
+  // CLEulerUpdate, after InvalidateDevice()) and then only enqueues timesteps; SyncCells() brings positions, last-step
+  // forces, Volume and SurfaceArea back into Cells (same checks and warnings as CLEulerUpdate).  Kre/Kat/PBC/L are read on
+  // every call; per-cell stiffnesses at upload time.  Same validation and exception types as CLEulerUpdate.
+  void StepResident(int nsteps, float dt);
+  void SyncCells();
+  void InvalidateDevice();
 
 private:
   std::shared_ptr<DeviceHandle3D> dev;  // created on first use; copies of a Tissue share it
@@ -49,6 +58,9 @@ public:
   void Disperse();
   void CLEulerUpdate(int nsteps, float dt);
   void AppendFrame(const std::string &path);  // extension, see Tissue3D::AppendFrame
+  void StepResident(int nsteps, float dt);     // extensions, see Tissue3D
+  void SyncCells();
+  void InvalidateDevice();
 
 private:
   int maxNV;

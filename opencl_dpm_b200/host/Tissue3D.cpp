@@ -15,10 +15,19 @@
 
 namespace DPM {
 
+// flat arrays in the C ABI's layout (float4-strided vertices, per-cell scalars), as the reference packs them (:137-197)
+struct Packed3D {
+  int NV = 0, NF = 0;
+  std::vector<uint32_t> faces;
+  std::vector<float> verts, forces, Kv, Ka, Ks, v0, a0, l0;
+};
+
 struct DeviceHandle3D {
   dpm3d_t *h = nullptr;
   int ncells = 0;
   std::vector<uint32_t> faces;
+  bool resident = false;  // the device holds the tissue's current state (StepResident)
+  Packed3D staging;       // host staging of the resident path
   ~DeviceHandle3D() {
     if (h) dpm3d_destroy(h);
   }
@@ -63,12 +72,8 @@ void Tissue3D::Disperse2D() {
   }
 }
 
-void Tissue3D::CLEulerUpdate(int nsteps, float dt) {
-  // the reference hard-codes Cell3D::NF / Cell3D::NV (:119-120); cells built with a subdivision level carry their own
-  const int NF = NCELLS > 0 && !Cells.empty() ? (int)Cells[0].nfaces() : (int)Cell3D::NF;
-  const int NV = NCELLS > 0 && !Cells.empty() ? (int)Cells[0].nverts() : (int)Cell3D::NV;
-
-  // ---- argument validation: same conditions, messages and exception types as reference :123-135
+// validation of the step arguments: same conditions, messages and exception types as reference :123-135
+static void validate_step(int nsteps, float dt, int NCELLS) {
   if (nsteps <= 0) {
     std::cerr << "[ERROR] Invalid nsteps: " << nsteps << std::endl;
     throw std::invalid_argument("nsteps must be positive");
@@ -82,8 +87,16 @@ void Tissue3D::CLEulerUpdate(int nsteps, float dt) {
     throw std::invalid_argument("NCELLS must be positive");
   }
 
-  // ---- pack: topology from Cells[0] only (:144-155), per-cell scalars and float4 vertices (:157-197)
-  std::vector<uint32_t> faces(3 * NF);
+}
+
+// topology from Cells[0] only (:144-155), per-cell scalars and float4 vertices (:157-197), with the reference's checks
+static void pack3d(const std::vector<Cell3D> &Cells, int NCELLS, Packed3D &P) {
+  // the reference hard-codes Cell3D::NF / Cell3D::NV (:119-120); cells built with a subdivision level carry their own
+  const int NF = P.NF = !Cells.empty() ? (int)Cells[0].nfaces() : (int)Cell3D::NF;
+  const int NV = P.NV = !Cells.empty() ? (int)Cells[0].nverts() : (int)Cell3D::NV;
+  std::vector<uint32_t> &faces = P.faces;
+  std::vector<float> &verts = P.verts, &forces = P.forces, &Kv = P.Kv, &Ka = P.Ka, &Ks = P.Ks, &v0 = P.v0, &a0 = P.a0, &l0 = P.l0;
+  faces.assign(3 * (size_t)NF, 0);
   for (int fi = 0; fi < NF; fi++) {
     const auto &f = Cells[0].Faces[fi];
     if (f[0] >= (unsigned)NV || f[1] >= (unsigned)NV || f[2] >= (unsigned)NV) {
@@ -93,8 +106,9 @@ void Tissue3D::CLEulerUpdate(int nsteps, float dt) {
     }
     faces[3 * fi] = f[0]; faces[3 * fi + 1] = f[1]; faces[3 * fi + 2] = f[2];
   }
-  std::vector<float> verts((size_t)NCELLS * NV * 4, 0.0f), forces((size_t)NCELLS * NV * 4, 0.0f);
-  std::vector<float> Kv(NCELLS), Ka(NCELLS), Ks(NCELLS), v0(NCELLS), a0(NCELLS), l0(NCELLS);
+  verts.assign((size_t)NCELLS * NV * 4, 0.0f);
+  forces.assign((size_t)NCELLS * NV * 4, 0.0f);
+  for (auto *x : {&Kv, &Ka, &Ks, &v0, &a0, &l0}) x->assign(NCELLS, 0.0f);
   for (int ci = 0; ci < NCELLS; ci++) {
     const Cell3D &c = Cells[ci];
     if ((int)c.nverts() != NV || (int)c.nfaces() != NF || (int)c.Forces.size() != NV) {
@@ -126,9 +140,49 @@ void Tissue3D::CLEulerUpdate(int nsteps, float dt) {
     }
   }
 
+}
+
+// flat -> Cells with the reference's post-conditions and checks (:477-521)
+static void unpack3d(std::vector<Cell3D> &Cells, int NCELLS, const Packed3D &P) {
+  const int NV = P.NV;
+  const std::vector<float> &verts = P.verts, &forces = P.forces;
+  for (int ci = 0; ci < NCELLS; ci++) {
+    for (int vi = 0; vi < NV; vi++) {
+      const float *pv = &verts[((size_t)ci * NV + vi) * 4], *pf = &forces[((size_t)ci * NV + vi) * 4];
+      for (int d = 0; d < 3; d++) {
+        if (!std::isfinite(pv[d])) {
+          std::cerr << "[ERROR] Non-finite result vertex at cell " << ci << ", vertex " << vi << ", coord " << d << ": "
+                    << pv[d] << std::endl;
+          throw std::runtime_error("Non-finite simulation results");
+        }
+        if (!std::isfinite(pf[d]))
+          std::cerr << "[WARNING] Non-finite force at cell " << ci << ", vertex " << vi << ", coord " << d << ": " << pf[d]
+                    << std::endl;
+      }
+      Cells[ci].Verts[vi] = {pv[0], pv[1], pv[2]};
+      Cells[ci].Forces[vi] = {pf[0], pf[1], pf[2]};
+    }
+    Cells[ci].Volume = Cells[ci].GetVolume();
+    Cells[ci].SurfaceArea = Cells[ci].GetSurfaceArea();
+    if (!std::isfinite(Cells[ci].Volume) || Cells[ci].Volume <= 0)
+      std::cerr << "[WARNING] Invalid volume for cell " << ci << ": " << Cells[ci].Volume << std::endl;
+    if (!std::isfinite(Cells[ci].SurfaceArea) || Cells[ci].SurfaceArea <= 0)
+      std::cerr << "[WARNING] Invalid surface area for cell " << ci << ": " << Cells[ci].SurfaceArea << std::endl;
+  }
+}
+
+void Tissue3D::CLEulerUpdate(int nsteps, float dt) {
+  validate_step(nsteps, dt, NCELLS);
+  Packed3D P;
+  pack3d(Cells, NCELLS, P);
+  const int NF = P.NF, NV = P.NV;
+  std::vector<uint32_t> &faces = P.faces;
+  std::vector<float> &verts = P.verts, &forces = P.forces, &Kv = P.Kv, &Ka = P.Ka, &Ks = P.Ks, &v0 = P.v0, &a0 = P.a0, &l0 = P.l0;
+
   // ---- device: one handle per tissue, re-created only if the size or topology changed
   try {
     if (!dev) dev = std::make_shared<DeviceHandle3D>();
+    dev->resident = false;  // this call re-uploads; afterwards callers may edit Cells, so nothing is assumed resident
     if (!dev->h || dev->ncells != NCELLS || dev->faces != faces) {
       if (dev->h) { dpm3d_destroy(dev->h); dev->h = nullptr; }
       if (dpm3d_create(&dev->h, 0, NCELLS, NV, NF, faces.data()) != DPM_OK) throw std::runtime_error(last_error());
@@ -155,30 +209,51 @@ void Tissue3D::CLEulerUpdate(int nsteps, float dt) {
     throw;
   }
 
-  // ---- unpack + checks (:477-521)
-  for (int ci = 0; ci < NCELLS; ci++) {
-    for (int vi = 0; vi < NV; vi++) {
-      const float *pv = &verts[((size_t)ci * NV + vi) * 4], *pf = &forces[((size_t)ci * NV + vi) * 4];
-      for (int d = 0; d < 3; d++) {
-        if (!std::isfinite(pv[d])) {
-          std::cerr << "[ERROR] Non-finite result vertex at cell " << ci << ", vertex " << vi << ", coord " << d << ": "
-                    << pv[d] << std::endl;
-          throw std::runtime_error("Non-finite simulation results");
-        }
-        if (!std::isfinite(pf[d]))
-          std::cerr << "[WARNING] Non-finite force at cell " << ci << ", vertex " << vi << ", coord " << d << ": " << pf[d]
-                    << std::endl;
+  unpack3d(Cells, NCELLS, P);
+}
+
+// ---- device-resident stepping (extension, see Tissue.hpp) -------------------------------------------------------
+void Tissue3D::InvalidateDevice() {
+  if (dev) dev->resident = false;
+}
+
+void Tissue3D::StepResident(int nsteps, float dt) {
+  validate_step(nsteps, dt, NCELLS);
+  try {
+    if (!dev) dev = std::make_shared<DeviceHandle3D>();
+    Packed3D &P = dev->staging;
+    if (!dev->resident) {
+      pack3d(Cells, NCELLS, P);
+      if (!dev->h || dev->ncells != NCELLS || dev->faces != P.faces) {
+        if (dev->h) { dpm3d_destroy(dev->h); dev->h = nullptr; }
+        if (dpm3d_create(&dev->h, 0, NCELLS, P.NV, P.NF, P.faces.data()) != DPM_OK) throw std::runtime_error(last_error());
+        dev->ncells = NCELLS;
+        dev->faces = P.faces;
       }
-      Cells[ci].Verts[vi] = {pv[0], pv[1], pv[2]};
-      Cells[ci].Forces[vi] = {pf[0], pf[1], pf[2]};
+      if (dpm3d_upload(dev->h, P.verts.data(), P.Kv.data(), P.Ka.data(), P.Ks.data(), P.v0.data(), P.a0.data(), P.l0.data()) != DPM_OK)
+        throw std::runtime_error(last_error());
+      dev->resident = true;
     }
-    Cells[ci].Volume = Cells[ci].GetVolume();
-    Cells[ci].SurfaceArea = Cells[ci].GetSurfaceArea();
-    if (!std::isfinite(Cells[ci].Volume) || Cells[ci].Volume <= 0)
-      std::cerr << "[WARNING] Invalid volume for cell " << ci << ": " << Cells[ci].Volume << std::endl;
-    if (!std::isfinite(Cells[ci].SurfaceArea) || Cells[ci].SurfaceArea <= 0)
-      std::cerr << "[WARNING] Invalid surface area for cell " << ci << ": " << Cells[ci].SurfaceArea << std::endl;
+    const unsigned mask = DPM3D_ALL | (attractionMethod == "AllVertAttraction" ? DPM3D_ATTRACT : 0u);
+    if (dpm3d_set_force_mask(dev->h, mask) != DPM_OK) throw std::runtime_error(last_error());
+    const int rc = dpm3d_step(dev->h, nsteps, dt, Kre, Kat, PBC, L);  // asynchronous: errors of the run surface in SyncCells
+    if (rc == DPM_ERR_INVALID_ARGUMENT) throw std::invalid_argument(last_error());
+    if (rc != DPM_OK) throw std::runtime_error(last_error());
+  } catch (const std::exception &e) {
+    std::cerr << "[ERROR] Exception caught: " << e.what() << std::endl;
+    throw;
   }
+}
+
+void Tissue3D::SyncCells() {
+  if (!dev || !dev->h || !dev->resident) return;  // nothing newer on the device than Cells
+  Packed3D &P = dev->staging;
+  if (dpm3d_download(dev->h, P.verts.data(), P.forces.data()) != DPM_OK) {
+    dev->resident = false;
+    std::cerr << "[ERROR] Exception caught: " << last_error() << std::endl;
+    throw std::runtime_error(last_error());
+  }
+  unpack3d(Cells, NCELLS, P);
 }
 
 }  // namespace DPM

@@ -40,6 +40,9 @@ PYBIND11_MODULE(clDPM, m) {
       .def_readwrite("Kat", &Tissue2D::Kat)
       .def("CLEulerUpdate", &Tissue2D::CLEulerUpdate)
       .def("AppendFrame", &Tissue2D::AppendFrame)
+      .def("StepResident", &Tissue2D::StepResident)
+      .def("SyncCells", &Tissue2D::SyncCells)
+      .def("InvalidateDevice", &Tissue2D::InvalidateDevice)
       .def("Disperse", &Tissue2D::Disperse);
 
   py::class_<Cell3D>(m, "Cell3D")
@@ -71,5 +74,9 @@ PYBIND11_MODULE(clDPM, m) {
       .def_readonly("PBC", &Tissue3D::PBC)
       .def("CLEulerUpdate", &Tissue3D::CLEulerUpdate)
       .def("AppendFrame", &Tissue3D::AppendFrame)
+      // extensions: device-resident stepping (no per-call upload/download), see Tissue.hpp
+      .def("StepResident", &Tissue3D::StepResident)
+      .def("SyncCells", &Tissue3D::SyncCells)
+      .def("InvalidateDevice", &Tissue3D::InvalidateDevice)
       .def("Disperse2D", &Tissue3D::Disperse2D);
 }

@@ -173,3 +173,27 @@ def test_coincident_vertices_of_two_cells_stay_finite():
         assert np.isfinite(Fref[m]).all() and np.isfinite(F[m]).all()
         assert np.abs(F - Fref)[m].max() <= H.force_tol(Fref)
     h.close()
+
+
+def test_step_resident_equals_repeated_cleulerupdate_2d():
+    """Tissue2D.StepResident / SyncCells (extension): same trajectory as repeated CLEulerUpdate calls, bit for bit."""
+    m = H.cldpm()
+
+    def tissue():
+        c = m.Cell2D(0.0, 0.0, 1.2, 25, 1.0)
+        c2 = m.Cell2D(0.0, 0.0, 1.2, 22, 1.3)
+        for x in (c, c2):
+            x.Ka, x.Kl, x.Kb = 0.1, 1.0, 0.05
+        T = m.Tissue2D([c, c2] * 12, 0.9)
+        T.Kre = 1.0
+        T.Kat = 0.5
+        H.reset_drand48()
+        T.Disperse()
+        return T
+
+    A, B = tissue(), tissue()
+    for _ in range(3):
+        A.CLEulerUpdate(20, 0.005)
+        B.StepResident(20, 0.005)
+    B.SyncCells()
+    assert np.array_equal(H.flat2d(A)["verts"], H.flat2d(B)["verts"])

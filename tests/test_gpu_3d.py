@@ -282,3 +282,43 @@ def test_cldpm_tissue3d_with_642_vertex_cells():
     assert np.abs(Fr).max() > 1.0
     assert np.abs(V - Vr[:, :3]).max() <= 4e-6
     assert np.abs(F - Fr[:, :3]).max() <= 4 * H.force_tol(Fr)
+
+
+def test_step_resident_equals_repeated_cleulerupdate():
+    """Extension: StepResident keeps the tissue on the device between calls (one upload, no per-call
+    download); 4 x 5 resident steps + SyncCells must equal 4 CLEulerUpdate(5) calls bit for bit (results do not depend on
+    the neighbour-list rebuild schedule), and editing Cells + InvalidateDevice() must be honoured."""
+    m = H.cldpm()
+
+    def tissue():
+        c = m.Cell3D([0.0, 0.0, 0.0], 1.0, 1.0)
+        c.Ka, c.Kv, c.Ks = 2.0, 5.0, 3.0
+        T = m.Tissue3D([c] * 16, 0.35)
+        T.Kre = 25.0
+        H.reset_drand48()
+        T.Disperse2D()
+        return T
+
+    A, B = tissue(), tissue()
+    for _ in range(4):
+        A.CLEulerUpdate(5, 0.01)
+        B.StepResident(5, 0.01)
+    B.SyncCells()
+    Va, Vb = H.flat3d(A)["verts"], H.flat3d(B)["verts"]
+    assert np.array_equal(Va, Vb)
+    Fa = np.concatenate([np.asarray(x.GetForces(), np.float32).T for x in A.Cells])
+    Fb = np.concatenate([np.asarray(x.GetForces(), np.float32).T for x in B.Cells])
+    assert np.array_equal(Fa, Fb) and np.abs(Fa).max() > 0
+    # edit the host copy, invalidate, continue: both paths see the edit
+    for T in (A, B):
+        cells = T.Cells
+        v = np.asarray(cells[3].Verts, np.float32) + np.float32(0.05)
+        cells[3].Verts = v.tolist()
+        T.Cells = cells
+    B.InvalidateDevice()
+    A.CLEulerUpdate(3, 0.01)
+    B.StepResident(3, 0.01)
+    B.SyncCells()
+    assert np.array_equal(H.flat3d(A)["verts"], H.flat3d(B)["verts"])
+    with pytest.raises(ValueError):
+        B.StepResident(0, 0.01)
