@@ -221,7 +221,8 @@ def main():
         # same per-cell work), so the N=1 D642 value is the single-GPU baseline of the same metric.
         args.workload = "D642" if world_env == 1 else "E642"
     if args.inner is None:
-        args.inner = 20 if not args.workload.startswith("E") else 10
+        # timesteps per CLEulerUpdate-equivalent call: the reference's own 3D demo advances 25 per call (test3D.py:20-22)
+        args.inner = 25 if not args.workload.startswith("E") else 10
 
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ci = blockIdx.x * W2D + warp;
+  griddep_launch();  // the next timestep's rebuild kernel may be scheduled (it waits for this grid's completion first)
   if (ci >= P.nc) return;  // whole warp leaves; no block-level barriers below
   const int S = P.S;
   // per warp: own ring, staged neighbour ring, force accumulators, found flags
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
 
   // ---- contacts: attraction (:250-267) and repulsion (:163-202) over the candidate cells, ascending id -----
   const int nchunk = (n + 31) >> 5;
+  griddep_wait();  // the candidate lists belong to the rebuild kernel ahead; everything above only needs the previous step's state
   const int ncand = min(P.cand_count[ci], P.K);
   const bool doAtt = (P.mask & DPM2D_ATTRACT) && (P.Kat != 0.0f);  // Kat == 0 adds exact zeros in the reference
   const bool doRep = (P.mask & DPM2D_REPEL);
@@ -561,8 +563,15 @@ int dpm2d_step(dpm2d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
     p.pos_in = h->pos[h->cur]; p.pos_out = h->pos[h->cur ^ 1];
     p.bnd_in = h->bnd[h->cur]; p.bnd_out = h->bnd[h->cur ^ 1];
     p.force_out = (s == nsteps - 1) ? h->force : nullptr;  // src/Tissue2D.cpp:223-227
-    dpm2d_step_kernel<<<(h->nc + W2D - 1) / W2D, T2D, smem, h->stream>>>(p);
-    DPM_CUDA_TRY(cudaGetLastError());
+    {  // programmatic dependent launch: ring staging, serial chains and shape forces overlap the rebuild kernel ahead
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)((h->nc + W2D - 1) / W2D)); cfg.blockDim = dim3(T2D); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      DPM_CUDA_TRY(cudaLaunchKernelEx(&cfg, dpm2d_step_kernel, p));
+    }
     h->cur ^= 1;
   }
   h->stats.steps += (uint64_t)nsteps;

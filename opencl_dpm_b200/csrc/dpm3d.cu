@@ -289,8 +289,9 @@ int dpm3d_create(dpm3d_t **out, int device, int ncells, int nv, int nf, const ui
   if (rc) return bail(rc);
   TRYB(cudaMalloc(&h->flag[0], (size_t)ncells * nf));
   TRYB(cudaMalloc(&h->flag[1], (size_t)ncells * nf));
-  TRYB(cudaMalloc(&h->unit_idx, sizeof(unsigned) * nvert));
-  TRYB(cudaMemset(h->unit_idx, 0, sizeof(unsigned) * nvert));
+  TRYB(cudaMalloc(&h->vlist, sizeof(uint2) * nvert));
+  TRYB(cudaMalloc(&h->vlist_cnt, sizeof(int) * ncells));
+  TRYB(cudaMemset(h->vlist_cnt, 0, sizeof(int) * ncells));
   TRYB(cudaMalloc(&h->unit_base, sizeof(int) * ncells));
   TRYB(cudaMalloc(&h->unit_cnt, sizeof(int) * ncells));
   TRYB(cudaMemset(h->unit_cnt, 0, sizeof(int) * ncells));
@@ -315,7 +316,7 @@ int dpm3d_destroy(dpm3d_t *h) {
   shard_free(h);
   void *ptrs[] = {h->pos[0], h->pos[1], h->force, h->bnd[0], h->bnd[1], h->cellA, h->cellB, h->faces, h->ring_nbr, h->ring_face,
                   h->valence, h->face_adj, h->ring_tab, h->ring_end, h->dir_table, h->st, h->bbox_lo, h->bbox_hi, h->bin_id, h->order, h->bin_count, h->bin_start, h->cand_count,
-                  h->cand, h->partial, h->chunk_sum, h->unit_rec, h->unit_w, h->unit_att, h->unit_base, h->unit_cnt, h->flag[0], h->flag[1], h->unit_idx};
+                  h->cand, h->partial, h->chunk_sum, h->unit_rec, h->unit_w, h->unit_att, h->unit_base, h->unit_cnt, h->flag[0], h->flag[1], h->vlist, h->vlist_cnt};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (h->h_cell) cudaFreeHost(h->h_cell);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -429,7 +430,7 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
   p.face_adj = h->face_adj; p.ring_tab = h->ring_tab; p.ring_end = h->ring_end; p.dir_table = h->dir_table;
   p.cand_count = h->cand_count; p.cand = h->cand; p.K = h->K;
   p.bbox_lo = h->bbox_lo; p.bbox_hi = h->bbox_hi; p.st = h->st;
-  p.unit_idx = h->unit_idx;
+  p.vlist = h->vlist; p.vlist_cnt = h->vlist_cnt;
   p.unit_rec = h->unit_rec; p.unit_w = h->unit_w; p.unit_att = h->unit_att; p.unit_base = h->unit_base; p.unit_cnt = h->unit_cnt; p.unit_cap = h->unit_cap;
   const bool repel = (h->mask & DPM3D_REPEL) && Kre != 0.0f;
   p.nc = h->nc; p.nv = h->nv; p.nf = h->nf; p.dt = dt; p.Kc = Kre; p.pbc = pbc; p.L = L;

@@ -28,7 +28,8 @@ struct dpm3d_ctx {
   uint16_t *dir_table = nullptr;   // rebuilt at every upload from cell 0
   std::vector<uint32_t> h_faces;
   unsigned char *flag[2] = {nullptr, nullptr};  // per-face flags, ping-pong with pos/bnd
-  unsigned *unit_idx = nullptr;                 // per-vertex (offset << 8 | count) into the cell's unit range
+  uint2 *vlist = nullptr;                       // per cell: its vertices that have units, (vertex, offset << 8 | count)
+  int *vlist_cnt = nullptr;
   int2 *unit_rec = nullptr;  // contact-unit queue (dpm3d_units_kernel -> dpm3d_contact_kernel -> dpm3d_step_kernel)
   float *unit_w = nullptr;
   float4 *unit_att = nullptr;  // allocated when DPM3D_ATTRACT is selected

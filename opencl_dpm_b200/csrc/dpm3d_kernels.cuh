@@ -39,7 +39,8 @@ struct Step3DParams {
   int ring_stride;
   const unsigned char *__restrict__ flag_in;  // [cell][nf] per-face flags of the CURRENT positions (bit0 facing the substrate,
   unsigned char *__restrict__ flag_out;       //   bit1 degenerate edge), written by the previous epilogue / bounds kernel
-  unsigned *__restrict__ unit_idx;            // [vertex] (offset within the cell's unit range) << 8 | count
+  uint2 *__restrict__ vlist;                  // [cell][<= nv] the cell's vertices that have units: (vertex, (offset within the
+  int *__restrict__ vlist_cnt;                //   cell's unit range) << 8 | count), and how many there are
   const ushort4 *__restrict__ face_adj;    // face across edge (a,b), (b,c), (c,a)
   const uint16_t *__restrict__ ring_tab;   // per face: faces in BFS (edge-adjacency) order, RING_TAB entries
   const uint8_t *__restrict__ ring_end;    // per face: cumulative end of rings 0..RING_MAX
@@ -147,8 +148,7 @@ __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)
 // griddep_wait() blocks until the preceding kernel of the stream has completed and its writes are visible (a no-op when
 // the kernel was launched without the attribute); griddep_launch() lets the following kernel's CTAs be scheduled once
 // every CTA of this grid has called it or exited.
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// (griddep_wait / griddep_launch live in dpm_common.cuh: the rebuild kernel in neighbor.cu is part of the chain)
 
 // 8-byte shared-memory load at a 32-bit shared address + immediate offset (one LDS.64, no generic addressing)
 template <int OFF>
@@ -373,7 +373,7 @@ template <bool ATT>
 __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams P) {
   __shared__ float4 sLo[UNITS_KMAX], sHi[UNITS_KMAX], sSph[UNITS_KMAX];
   __shared__ int sCand[UNITS_KMAX];
-  __shared__ int sWarp[UNITS_THREADS / 32];
+  __shared__ int sWarp[UNITS_THREADS / 32], sWarpV[UNITS_THREADS / 32];
   __shared__ int sBase;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ci = blockIdx.x, nv = P.nv, K = P.K;
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams
     nact += ov ? 1 : 0;
   }
   if (__syncthreads_or(nact) == 0) {  // no neighbour's box reaches this cell
-    if (tid == 0) { P.unit_base[ci] = 0; P.unit_cnt[ci] = 0; }
+    if (tid == 0) { P.unit_base[ci] = 0; P.unit_cnt[ci] = 0; P.vlist_cnt[ci] = 0; }
     return;
   }
   // One pass of tests: with at most 32 candidates (the default capacity) the survivors of a vertex are kept as a bit mask
@@ -460,15 +460,25 @@ __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams
       cnt += cntj[j];
     }
   }
-  // exclusive scan of the per-thread counts
-  int incl = cnt;
+  // exclusive scans of the per-thread counts: units, and vertices that have any
+  int nvh = 0;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
-  if (lane == 31) sWarp[warp] = incl;
+  for (int j = 0; j < UNITS_VPT; j++) nvh += cntj[j] > 0 ? 1 : 0;
+  int incl = cnt, vincl = nvh;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, incl, o), m = __shfl_up_sync(0xffffffffu, vincl, o);
+    if (lane >= o) { incl += n; vincl += m; }
+  }
+  if (lane == 31) { sWarp[warp] = incl; sWarpV[warp] = vincl; }
   __syncthreads();
-  int woff = 0, total = 0;
+  int woff = 0, total = 0, vwoff = 0, vtotal = 0;
 #pragma unroll
-  for (int w = 0; w < UNITS_THREADS / 32; w++) { const int c = sWarp[w]; if (w < warp) woff += c; total += c; }
+  for (int w = 0; w < UNITS_THREADS / 32; w++) {
+    const int c = sWarp[w], d = sWarpV[w];
+    if (w < warp) { woff += c; vwoff += d; }
+    total += c; vtotal += d;
+  }
   if (tid == 0) {
     int base = 0;
     if (total > 0) {
@@ -479,14 +489,17 @@ __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams
     sBase = base;
     P.unit_base[ci] = base < 0 ? 0 : base;
     P.unit_cnt[ci] = base < 0 ? 0 : total;
+    P.vlist_cnt[ci] = base < 0 ? 0 : vtotal;
   }
   __syncthreads();
-  {  // per-vertex (offset, count) so that the step kernel finds a vertex's units without scanning
+  {  // the cell's vertices that have units, with (offset, count) into its unit range: all the step kernel has to visit
     int off = woff + incl - cnt;
+    uint2 *vl = P.vlist + (size_t)ci * nv + (vwoff + vincl - nvh);
 #pragma unroll
     for (int j = 0; j < UNITS_VPT; j++) {
       const int v = tid + j * UNITS_THREADS;
-      if (v < nv) { P.unit_idx[(size_t)ci * nv + v] = ((unsigned)off << 8) | (unsigned)min(cntj[j], 255); off += cntj[j]; }
+      if (v < nv && cntj[j] > 0) *vl++ = make_uint2((unsigned)v, ((unsigned)off << 8) | (unsigned)min(cntj[j], 255));
+      off += cntj[j];
     }
   }
   if (total == 0 || sBase < 0) return;
@@ -983,20 +996,22 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
   const int ubase = (doRep || doAtt) ? P.unit_base[ci] : 0;
   const float *uw = P.unit_w + ubase;
   const float4 *ua = P.unit_att + ubase;
-  VertPartial vp;
-  vp.init();
-  for (int v = tid; v < nv; v += STEP_THREADS) {
-    float4 F = sF[v];
-    float4 np = sP[v];
-    // fold this vertex's evaluated contact units (ordered by ascending neighbour id: the reference's cj order)
-    if (ucnt > 0) {
-      const unsigned ui = P.unit_idx[(size_t)ci * nv + v];
-      const int un = ui & 0xffu, uo = ui >> 8;
+  // fold the evaluated contact units into the forces of the few vertices that have any (the units kernel's compact list;
+  // a vertex's units are ordered by ascending neighbour id: the reference's cj order), before the Euler loop
+  if (ucnt > 0) {  // uniform over the CTA
+    const int nvl = P.vlist_cnt[ci];
+    const uint2 *vl = P.vlist + (size_t)ci * nv;
+    for (int i = tid; i < nvl; i += STEP_THREADS) {
+      const uint2 e = vl[i];
+      const int v = (int)e.x, un = (int)(e.y & 0xffu), uo = (int)(e.y >> 8);
+      float4 F = sF[v];
+      const float4 np = sP[v];
       float3 dir = f3(0.f, 0.f, 0.f);
       bool have = false;
       if (doAtt)  // AllVertAttraction (:313-364): the units' gathered vertex-vertex terms
         DPM_UNROLL(1)
         for (int u = uo; u < uo + un; u++) { const float4 a = ua[u]; F.x += a.x; F.y += a.y; F.z += a.z; }
+      DPM_UNROLL(1)
       for (int u = uo; u < uo + un; u++) {
         const float wn = uw[u];
         if (doRep && !(fabsf(wn) < 1e-6f)) {  // :302-308
@@ -1010,7 +1025,15 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
           F.x += mg * dir.x; F.y += mg * dir.y; F.z += mg * dir.z;
         }
       }
+      sF[v] = F;
     }
+    __syncthreads();
+  }
+  VertPartial vp;
+  vp.init();
+  for (int v = tid; v < nv; v += STEP_THREADS) {
+    const float4 F = sF[v];
+    float4 np = sP[v];
     np.x += F.x * P.dt; np.y += F.y * P.dt; np.z += F.z * P.dt;
     np.w = 0.f;
     if (P.force_out) P.force_out[(size_t)ci * nv + v] = F;
@@ -1020,6 +1043,7 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
   fence_async_smem();  // this thread's sP writes -> visible to the bulk store issued below
   __syncthreads();
   if (tid == 0) bulk_s2g(P.pos_out + (size_t)ci * nv, sP, (unsigned)(sizeof(float4) * nv));
+  griddep_launch();  // the next timestep's rebuild kernel may be scheduled; it waits for this grid's completion before it reads anything
 
   // ---- next step's per-cell scalars from the NEW positions --------------------------------------------------
   CellTopo T;

@@ -80,6 +80,12 @@ int rebuild_max_grid(int device);
 
 // ---- small device helpers -----------------------------------------------------
 #ifdef __CUDACC__
+// Programmatic dependent launch (kernels chained with cudaLaunchAttributeProgrammaticStreamSerialization):
+// griddep_wait() blocks until the preceding kernel of the stream has completed and its writes are visible (a no-op when
+// the kernel was launched without the attribute); griddep_launch() lets the following kernel's CTAs be scheduled once
+// every CTA of this grid has called it or exited.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -8,8 +8,12 @@
 // (oracle_cell_list); tests require bit-exact equality, so every floating-point
 // operation below is an explicitly rounded single IEEE op (__f*_rn), never an FMA.
 //
-// One cooperative kernel does the whole rebuild; it returns immediately when the
-// device-side flag NbrState::rebuild is 0, so it can be enqueued before every step.
+// One kernel does the whole rebuild; it returns immediately when the device-side flag
+// NbrState::rebuild is 0, so it is enqueued before every step.  It runs as ONE thread-block
+// cluster (8 CTAs x 512 threads, cluster-wide barriers between the phases) instead of a
+// cooperative grid: a cluster launch is an ordinary launch, so the per-step no-op costs what
+// any small kernel costs and it can be chained to its neighbours in the stream with
+// programmatic dependent launch (a cooperative launch cost ~6 us per step and broke the chain).
 #include <cooperative_groups.h>
 
 #include "dpm_common.cuh"
@@ -19,7 +23,8 @@ namespace cg = cooperative_groups;
 namespace dpm {
 
 #define NBMAX 1024
-#define RB_THREADS 256
+#define RB_THREADS 512
+#define RB_CLUSTER 8  // portable cluster size
 #define KMAX 128
 
 __device__ __forceinline__ float centre_rn(float lo, float hi) { return __fmul_rn(0.5f, __fadd_rn(lo, hi)); }
@@ -100,10 +105,15 @@ __device__ __forceinline__ bool axis_far(float li, float hi, float lj, float hj,
 }
 
 __global__ void __launch_bounds__(RB_THREADS) nbr_rebuild_kernel(NbrBuffers nb) {
+  // Programmatic dependent launch: the kernel ahead in the stream (the previous timestep's step kernel, or the upload's
+  // bounds kernel) must be complete before its rebuild flag and bounds are read; only then may the kernels behind be
+  // scheduled (they prefetch the state that kernel wrote, and wait for THIS kernel before they touch the lists).
+  griddep_wait();
+  griddep_launch();
   if (blockIdx.x == 0 && threadIdx.x == 0) nb.st->unit_total = 0;  // first kernel of every step: reset the contact-unit queue
-  if (nb.st->rebuild == 0) return;  // uniform across the grid: nobody reaches a grid sync
+  if (nb.st->rebuild == 0) return;  // uniform across the cluster: nobody reaches a barrier
   if (nb.nc_dev) nb.nc = *nb.nc_dev;
-  cg::grid_group grid = cg::this_grid();
+  cg::cluster_group grid = cg::this_cluster();  // the launch is one cluster: gridDim.x == cluster size
   const int tid = threadIdx.x;
   const int gtid = blockIdx.x * blockDim.x + tid;
   const int nthreads = gridDim.x * blockDim.x;
@@ -329,18 +339,21 @@ __global__ void __launch_bounds__(RB_THREADS) nbr_rebuild_kernel(NbrBuffers nb) 
 }
 
 int rebuild_max_grid(int device) {
-  int sms = 0, per = 0;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, nbr_rebuild_kernel, RB_THREADS, 0);
-  if (per < 1) per = 1;
-  if (per > 2) per = 2;
-  return sms * per;
+  (void)device;
+  return RB_CLUSTER;  // CTAs of the one cluster (sizes of NbrBuffers::partial / chunk_sum)
 }
 
 cudaError_t launch_rebuild(const NbrBuffers &nb, cudaStream_t stream, int coop_grid) {
-  NbrBuffers arg = nb;
-  void *args[] = {&arg};
-  return cudaLaunchCooperativeKernel((void *)nbr_rebuild_kernel, dim3(coop_grid), dim3(RB_THREADS), args, 0, stream);
+  (void)coop_grid;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(RB_CLUSTER); cfg.blockDim = dim3(RB_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = RB_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, nbr_rebuild_kernel, nb);
 }
 
 }  // namespace dpm
