@@ -60,7 +60,7 @@ def build_cldpm(force: bool = False) -> str:
     srcs = sorted(os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".cpp"))
     if not force and _newer(out, _deps(HOST) + [LIB]):
         return out
-    cmd = [CXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", out] + srcs + [
+    cmd = [CXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-pthread", "-o", out] + srcs + [
         "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"], "-I", HOST,
         "-I", os.path.join(HERE, "..", "include"), "-L", HERE, "-ldpm_b200", "-Wl,-rpath,$ORIGIN",
     ]

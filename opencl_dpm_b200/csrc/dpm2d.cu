@@ -77,7 +77,7 @@ __device__ __forceinline__ bool edge_toggles(float2 p, float2 vi, float2 vj, boo
 // for every (vertex, candidate cell) pair that survives the exact culls, the 32 lanes split the candidate's ring —
 // edges of the even-odd test (parity of the ballots) and vertices of the attraction sum (nonzero terms folded in
 // ascending vertex order, the reference's order) — instead of each lane looping over the whole ring on its own.
-__global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
+__global__ void __launch_bounds__(T2D, 7) dpm2d_step_kernel(Step2DParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ci = blockIdx.x * W2D + warp;
@@ -89,9 +89,9 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
   float2 *sN = sV + S;
   float2 *sF = sN + S;
   unsigned char *sFound = reinterpret_cast<unsigned char *>(reinterpret_cast<float2 *>(smem_raw) + (size_t)W2D * 3 * S) + (size_t)warp * S;
-  // the candidate's vertices near this cell (attraction), ascending; after the found flags, 2-byte aligned
-  unsigned short *sNear = reinterpret_cast<unsigned short *>(reinterpret_cast<unsigned char *>(reinterpret_cast<float2 *>(smem_raw) + (size_t)W2D * 3 * S) +
-                                                             (((size_t)W2D * S + 1) & ~(size_t)1)) + (size_t)warp * S;
+  // the candidate's vertices near this cell (attraction), ascending vertex order; after the found flags, 8-byte aligned
+  float2 *sNear = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(reinterpret_cast<float2 *>(smem_raw) + (size_t)W2D * 3 * S) +
+                                             (((size_t)W2D * S + 7) & ~(size_t)7)) + (size_t)warp * S;
   const int n = P.nv[ci];
   const float4 cA = P.cellA[ci], cB = P.cellB[ci];
   const float Ka = cA.x, Kl = cA.y, Kb = cA.z, a0 = cA.w, l0 = cB.x, r0 = cB.y;
@@ -212,15 +212,16 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
             for (int base = 0; base < nj; base += 32) {
               const int vj = base + lane;
               bool near = false;
+              float2 q = make_float2(0.f, 0.f);
               if (vj < nj) {
-                const float2 q = sN[vj];
+                q = sN[vj];
                 float dx = q.x - cxi, dy = q.y - cyi;
                 if (P.pbc) { dx -= P.L * roundf(dx * invL); dy -= P.L * roundf(dy * invL); }  // cull only, see above
                 const float ax = fmaxf(fabsf(dx) - hxi, 0.0f), ay = fmaxf(fabsf(dy) - hyi, 0.0f);
                 near = !own_cull_ok || (ax * ax + ay * ay <= l0 * l0 * 1.0001f + 1e-12f);
               }
               const unsigned nb = __ballot_sync(0xffffffffu, near);
-              if (near) sNear[nnear + __popc(nb & ((1u << lane) - 1u))] = (unsigned short)vj;
+              if (near) sNear[nnear + __popc(nb & ((1u << lane) - 1u))] = q;
               nnear += __popc(nb);
             }
             __syncwarp();
@@ -228,22 +229,24 @@ __global__ void __launch_bounds__(T2D) dpm2d_step_kernel(Step2DParams P) {
           }
           if (wantAtt && nnear > 0) {
             float2 f = sF[vi];
-            const float kn = P.Kat / (float)n;
-            const float l0sq_hi = l0 * l0 * 1.00001f;  // prefilter on the squared distance; the reference's test follows
+            // Forces[index] += (Kat / NV * dist / l0) * normalize(rij)   (:263-264): dist cancels, the term is (Kat / NV / l0) * rij
+            // (and 0 for rij = 0, as OpenCL's normalize(0) = 0 gives); evaluated in that form, a few ulp from the literal one.
+            // The cutoff dist < l0 is the reference's own test: decided on the squared distance, with the sqrt only in the
+            // narrow band where the two could disagree.
+            const float c = P.Kat / (float)n / l0;
+            const float l0sq = l0 * l0, l0sq_lo = l0sq * 0.99999f, l0sq_hi = l0sq * 1.00001f;
             for (int t = 0; t < nnear; t++) {
-              const float2 q = sN[sNear[t]];
+              const float2 q = sNear[t];
               float rx = q.x - p.x, ry = q.y - p.y;
               if (P.pbc) {  // rij -= L * round(rij / L)  (:254-256); a no-op unless |r| > L/2
                 if (fabsf(rx) > halfL) rx -= P.L * roundf(rx / P.L);
                 if (fabsf(ry) > halfL) ry -= P.L * roundf(ry / P.L);
               }
               const float d2 = rx * rx + ry * ry;
-              if (d2 < l0sq_hi && d2 != 0.0f) {  // OpenCL normalize(0) = 0 (two coinciding vertices; measured on the reference's runtime)
-                const float dist = sqrtf(d2);
-                if (dist < l0) {                      // :258-262
-                  const float ftmp = kn * dist / l0;  // :263
-                  f.x += ftmp * (rx / dist);          // Forces[index] += ftmp * normalize(rij), in vj order (:264)
-                  f.y += ftmp * (ry / dist);
+              if (d2 < l0sq_hi) {
+                if (d2 < l0sq_lo || sqrtf(d2) < l0) {  // :258-262
+                  f.x += c * rx;
+                  f.y += c * ry;
                 }
               }
             }
@@ -356,7 +359,7 @@ struct dpm2d_ctx {
 
 namespace {
 // per warp: own ring, staged neighbour ring, force accumulators (float2 each) + found flags (bytes)
-inline size_t smem2d_bytes(int S) { return (sizeof(float2) * 3 + 1 + 2) * (size_t)S * W2D + 32; }
+inline size_t smem2d_bytes(int S) { return (sizeof(float2) * 4 + 1) * (size_t)S * W2D + 32; }
 
 struct DeviceGuard2 {
   int prev = -1;

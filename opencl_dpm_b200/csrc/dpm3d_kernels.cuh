@@ -1,19 +1,26 @@
-// dpm3d_kernels.cuh — fused 3D force + integrate step for sm_100a.
+// dpm3d_kernels.cuh — the 3D force + integrate timestep for sm_100a.
 //
 // Replaces the six per-step OpenCL kernels of shaders/Cell3D_Kernel.cl
 // (ClearForces :366, VolumeForceUpdate :66, SurfaceAreaForceUpdate :114,
-//  StickToSurface :180, RepellingForces :251, EulerPosition :371) and their
-// enqueue sequence (src/Tissue3D.cpp:372-423) by ONE kernel per timestep:
+//  StickToSurface :180, RepellingForces :251, EulerPosition :371 — and, opt-in,
+//  AllVertAttraction :313) and their enqueue sequence (src/Tissue3D.cpp:372-423) by three
+// kernels per timestep, chained with programmatic dependent launch behind the neighbour
+// rebuild kernel of neighbor.cu:
 //
-//   CTA = one cell.  The cell's vertex ring (float4) is staged in shared memory,
-//   shape forces are GATHERED per vertex over a constant ring adjacency (no float
-//   atomics, unlike atomic_add_f :10-32), the repulsion evaluates the winding number
-//   only for (vertex, neighbour-cell) pairs that survive the cell list + an exact
-//   AABB / bounding-sphere cull, one warp per pair with the neighbour's unit vectors
-//   staged in shared memory, and the Euler update writes the other position buffer
-//   (all forces of a step use start-of-step positions).  The epilogue
-//   produces next step's per-cell bounds (AABB, COM, r^2max) and raises the
-//   rebuild flag when a cell leaves its build-time box.
+//   dpm3d_units_kernel    CTA = one cell: every vertex against the padded bounding box and
+//                         sphere of each cell-list candidate -> "contact units" (vertex,
+//                         neighbour) in one global queue (exact cull);
+//   dpm3d_contact_kernel  8 lanes per unit, load-balanced over the whole GPU: the reference's
+//                         winding number of the unit by the exact decomposition
+//                         w_ref = W - sum(skipped faces)  (walk to the pierced face + ring search);
+//   dpm3d_step_kernel     CTA = one cell.  The cell's vertices (float4) arrive in shared memory by
+//                         a bulk async copy; shape forces are GATHERED per vertex over a constant
+//                         ring adjacency (no float atomics, unlike atomic_add_f :10-32); the units'
+//                         weights are folded in; the Euler update writes the other position buffer
+//                         (all forces of a step use start-of-step positions); the epilogue
+//                         produces next step's per-cell bounds (AABB, COM, volume, r^2max, contact pad,
+//                         star-shape flag, per-face flags) and raises the rebuild flag when a cell
+//                         leaves its build-time box.
 //
 // Numerical contract: per-cell COM and signed-volume sums are
 // evaluated in the reference's serial order with individually rounded operations,
@@ -80,7 +87,6 @@ struct Step3DParams {
 #ifndef DPM_STEP_MINB
 #define DPM_STEP_MINB 1  // CTAs per SM promised to ptxas for the step kernel (1 = no register cap); see profiles/ for the sweep
 #endif
-constexpr int UNIT_CAP_FACTOR = 2;  // unit list capacity = factor * THREADS
 constexpr int BND = 4;              // float4 per cell in the bounds arrays:
                                     //   (lo.xyz, r2max) (hi.xyz, contact pad) (com.xyz, volume) (r2min, star flag, 0, 0)
 // The reference skips faces with denom < 1e-8 (shaders/Cell3D_Kernel.cl:293-295), i.e. every face that subtends

@@ -5,9 +5,12 @@
 // validation, exceptions, stdout/stderr messages and post-conditions (:118-522) — but the
 // OpenCL program build, the ten cl::Buffers, six cl::Kernels and the per-step enqueue loop
 // (:199-470) are ONE call into dpm3d_euler_update (include/dpm_b200.h).
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <iostream>
 #include <stdexcept>
+#include <thread>
 
 #include "Tissue.hpp"
 #include "disperse.hpp"
@@ -72,6 +75,25 @@ void Tissue3D::Disperse2D() {
   }
 }
 
+// Packing and unpacking walk every vertex of every cell on the host (AoS <-> the C ABI's flat arrays); for BASELINE-size
+// tissues (millions of vertices) that costs more than the device call itself.  Cells are independent, so ranges of cells
+// go to a few threads.  The threads only run the silent happy path: any condition that would make the reference print or
+// throw (:149-190, :477-521) sets `bad`, and the caller then repeats the pass serially with the original, ordered
+// messages and exceptions.
+template <typename Fn>
+static void parallel_cells(int ncells, size_t work_per_cell, Fn &&fn) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int nt = (int)std::min<size_t>(std::min<unsigned>(hw ? hw : 1u, 16u), (size_t)ncells * work_per_cell / 100000);
+  if (nt < 2) { fn(0, ncells); return; }
+  std::vector<std::thread> th;
+  const int chunk = (ncells + nt - 1) / nt;
+  for (int t = 0; t < nt; t++) {
+    const int c0 = t * chunk, c1 = std::min(ncells, c0 + chunk);
+    if (c0 < c1) th.emplace_back([&fn, c0, c1] { fn(c0, c1); });
+  }
+  for (auto &x : th) x.join();
+}
+
 // validation of the step arguments: same conditions, messages and exception types as reference :123-135
 static void validate_step(int nsteps, float dt, int NCELLS) {
   if (nsteps <= 0) {
@@ -109,6 +131,28 @@ static void pack3d(const std::vector<Cell3D> &Cells, int NCELLS, Packed3D &P) {
   verts.assign((size_t)NCELLS * NV * 4, 0.0f);
   forces.assign((size_t)NCELLS * NV * 4, 0.0f);
   for (auto *x : {&Kv, &Ka, &Ks, &v0, &a0, &l0}) x->assign(NCELLS, 0.0f);
+  {  // threaded happy path; anything the checks below would report makes the serial pass run instead
+    std::atomic<bool> bad{false};
+    parallel_cells(NCELLS, (size_t)NV, [&](int c0, int c1) {
+      for (int ci = c0; ci < c1 && !bad.load(std::memory_order_relaxed); ci++) {
+        const Cell3D &c = Cells[ci];
+        bool ok = (int)c.nverts() == NV && (int)c.nfaces() == NF && (int)c.Forces.size() == NV && c.Kv > 0 && c.Ka > 0 && c.Ks > 0 &&
+                  c.v0 > 0 && c.a0 > 0;
+        if (ok) {
+          Kv[ci] = c.Kv; Ka[ci] = c.Ka; Ks[ci] = c.Ks; v0[ci] = c.v0; a0[ci] = c.a0;
+          l0[ci] = sqrt(4.0f * c.a0) / sqrt(3.0f);
+          float *dst = &verts[(size_t)ci * NV * 4];
+          for (int vi = 0; vi < NV; vi++, dst += 4) {
+            const auto &q = c.Verts[vi];
+            ok = ok && std::isfinite(q[0]) && std::isfinite(q[1]) && std::isfinite(q[2]);
+            dst[0] = q[0]; dst[1] = q[1]; dst[2] = q[2];
+          }
+        }
+        if (!ok) bad.store(true, std::memory_order_relaxed);
+      }
+    });
+    if (!bad.load()) return;
+  }
   for (int ci = 0; ci < NCELLS; ci++) {
     const Cell3D &c = Cells[ci];
     if ((int)c.nverts() != NV || (int)c.nfaces() != NF || (int)c.Forces.size() != NV) {
@@ -146,6 +190,27 @@ static void pack3d(const std::vector<Cell3D> &Cells, int NCELLS, Packed3D &P) {
 static void unpack3d(std::vector<Cell3D> &Cells, int NCELLS, const Packed3D &P) {
   const int NV = P.NV;
   const std::vector<float> &verts = P.verts, &forces = P.forces;
+  {  // threaded happy path; anything the checks below would report makes the serial pass run instead
+    std::atomic<bool> bad{false};
+    parallel_cells(NCELLS, (size_t)NV * 3, [&](int c0, int c1) {
+      for (int ci = c0; ci < c1 && !bad.load(std::memory_order_relaxed); ci++) {
+        Cell3D &c = Cells[ci];
+        bool ok = true;
+        const float *pv = &verts[(size_t)ci * NV * 4], *pf = &forces[(size_t)ci * NV * 4];
+        for (int vi = 0; vi < NV; vi++, pv += 4, pf += 4) {
+          ok = ok && std::isfinite(pv[0]) && std::isfinite(pv[1]) && std::isfinite(pv[2]) && std::isfinite(pf[0]) && std::isfinite(pf[1]) &&
+               std::isfinite(pf[2]);
+          c.Verts[vi] = {pv[0], pv[1], pv[2]};
+          c.Forces[vi] = {pf[0], pf[1], pf[2]};
+        }
+        c.Volume = c.GetVolume();
+        c.SurfaceArea = c.GetSurfaceArea();
+        ok = ok && std::isfinite(c.Volume) && c.Volume > 0 && std::isfinite(c.SurfaceArea) && c.SurfaceArea > 0;
+        if (!ok) bad.store(true, std::memory_order_relaxed);
+      }
+    });
+    if (!bad.load()) return;
+  }
   for (int ci = 0; ci < NCELLS; ci++) {
     for (int vi = 0; vi < NV; vi++) {
       const float *pv = &verts[((size_t)ci * NV + vi) * 4], *pf = &forces[((size_t)ci * NV + vi) * 4];

@@ -322,3 +322,31 @@ def test_step_resident_equals_repeated_cleulerupdate():
     assert np.array_equal(H.flat3d(A)["verts"], H.flat3d(B)["verts"])
     with pytest.raises(ValueError):
         B.StepResident(0, 0.01)
+
+
+def test_threaded_pack_unpack_equals_flat_path():
+    """A tissue large enough for the host classes' threaded pack/unpack (> 2e5 vertices): Tissue3D.CLEulerUpdate must
+    equal the C ABI driven with the same flat arrays, bit for bit (positions, last-step forces, Volume)."""
+    from opencl_dpm_b200 import Dpm3D
+
+    m = H.cldpm()
+    c = m.Cell3D([0.0, 0.0, 1.0], 1.0, 1.0)
+    c.Ka, c.Kv, c.Ks = 2.0, 5.0, 3.0
+    n = 1400
+    T = m.Tissue3D([c] * n, 0.35)
+    T.Kre = 25.0
+    H.reset_drand48()
+    T.Disperse2D()
+    d = H.flat3d(T)
+    P = H.params3d(n, 1.0, 1.0, 5.0, 2.0, 3.0)
+    T.CLEulerUpdate(4, 0.01)
+    out = T.Cells
+    Vc = np.concatenate([np.asarray(x.Verts, np.float32) for x in out])
+    Fc = np.concatenate([np.asarray(x.GetForces(), np.float32).T for x in out])
+    h = Dpm3D(n, 162, d["faces"])
+    V = d["verts"].copy()
+    F = np.zeros_like(V)
+    h.euler_update(V, *[P[k] for k in PKEYS], 4, 0.01, 25.0, 0.0, d["PBC"], float(d["L"]), forces_out=F)
+    h.close()
+    assert np.array_equal(Vc, V[:, :3]) and np.array_equal(Fc, F[:, :3])
+    assert abs(out[5].GetVolume() - 4.0) < 0.5

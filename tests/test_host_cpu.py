@@ -254,3 +254,29 @@ def test_trajectory_writer_roundtrip(tmp_path):
     assert np.array_equal(r2["frames"][0, 1, :22], np.asarray(T2.Cells[1].Verts, np.float32)) and not r2["frames"][0, 1, 22:].any()
     with pytest.raises(RuntimeError):
         T.AppendFrame(p2)  # a 3D tissue into a 2D file
+
+
+def test_threaded_pack_keeps_the_reference_validation_errors():
+    """Tissues above ~2e5 vertices are packed by several threads (host/Tissue3D.cpp:parallel_cells); the threads only run
+    the silent happy path, so a bad input must still raise the reference's error for the FIRST offending cell
+    (src/Tissue3D.cpp:157-190), from the serial pass."""
+    import helpers as H
+
+    m = H.cldpm()
+    c = m.Cell3D([0.0, 0.0, 0.0], 1.0, 1.0)
+    c.Ka, c.Kv, c.Ks = 2.0, 5.0, 3.0
+    n = 1400  # x 162 vertices = 226,800 > the threading threshold
+    T = m.Tissue3D([c] * n, 0.35)
+    T.Kre = 25.0
+    cells = T.Cells
+    v = np.asarray(cells[900].Verts, np.float32)
+    v[17, 1] = np.nan
+    cells[900].Verts = v.tolist()
+    cells[1200].Kv = -1.0  # a later problem of another kind: must not be the one reported
+    T.Cells = cells
+    with pytest.raises(RuntimeError, match="Non-finite vertex coordinates"):
+        T.CLEulerUpdate(1, 0.01)
+    cells[900].Verts = np.nan_to_num(v).tolist()
+    T.Cells = cells
+    with pytest.raises(RuntimeError, match="Invalid spring constants"):
+        T.CLEulerUpdate(1, 0.01)
