@@ -265,7 +265,8 @@ def main():
         if sharded:
             from opencl_dpm_b200 import shard
 
-            h.shard_init(rank, world, shard.broadcast_unique_id(rank), max_ghost=2 * 512)
+            h.shard_init(rank, world, shard.broadcast_unique_id(rank), max_ghost=768 if world > 2 else 1280)
+            # one lattice column (512 cells) per slab face + headroom; with 2 ranks the single peer is both neighbours
             h.set_global_ids(d["gid"])
         h.set_stream(stream.cuda_stream)
         params = [d[k] for k in PK3]

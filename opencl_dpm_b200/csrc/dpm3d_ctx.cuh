@@ -66,6 +66,8 @@ struct dpm3d_ctx {
   int *gid = nullptr;  // [nslots] global cell ids (owned: set by dpm3d_set_global_ids, ghosts: from the halo messages)
   dpm::ShardDev *sd = nullptr;
   float *gather_send = nullptr, *gather_all = nullptr;
+  float *prep_partial = nullptr;  // per-CTA partials of the per-rank summary kernel
+  unsigned *prep_ticket = nullptr;
   unsigned char *sendbuf[2] = {nullptr, nullptr}, *recvbuf[2] = {nullptr, nullptr};
   int *sendlist[2] = {nullptr, nullptr};
   size_t msg_bytes = 0;

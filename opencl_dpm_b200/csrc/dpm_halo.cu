@@ -23,6 +23,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -86,10 +88,15 @@ __host__ __device__ inline size_t msg_off_pos(int C) { return msg_off_bnd(C) + s
 __host__ __device__ inline size_t msg_size(int C, int nv) { return msg_off_pos(C) + sizeof(float4) * (size_t)nv * C; }
 
 // ---- 1. per-rank summary -------------------------------------------------------------------------------------
-__global__ void shard_prepare_kernel(const float4 *bnd, int n_own, const NbrState *st, float *out, float att_pad_scale) {
+// PREP_CTAS CTAs reduce their share of the owned cells; the last one to finish (ticket counter) folds the partials and
+// writes the rank's summary.  (A single CTA took 264 us for 131,072 cells: it was the largest part of the halo step.)
+constexpr int PREP_CTAS = 128;
+__global__ void __launch_bounds__(256) shard_prepare_kernel(const float4 *bnd, int n_own, const NbrState *st, float *out, float att_pad_scale,
+                                                             float *partial /*[PREP_CTAS][4]*/, unsigned *ticket) {
   __shared__ float s[8][4];
+  __shared__ bool last;
   float rlo = INFINITY, rhi = -INFINITY, ext = 0.f, pad = 0.f;
-  for (int c = threadIdx.x; c < n_own; c += blockDim.x) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_own; c += gridDim.x * blockDim.x) {
     const float4 lo = bnd[BND * (size_t)c], hi = bnd[BND * (size_t)c + 1];
     rlo = fminf(rlo, lo.x); rhi = fmaxf(rhi, hi.x);
     ext = fmaxf(ext, fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z)));
@@ -105,10 +112,22 @@ __global__ void shard_prepare_kernel(const float4 *bnd, int n_own, const NbrStat
       s[0][0] = fminf(s[0][0], s[i][0]); s[0][1] = fmaxf(s[0][1], s[i][1]);
       s[0][2] = fmaxf(s[0][2], s[i][2]); s[0][3] = fmaxf(s[0][3], s[i][3]);
     }
-    out[0] = st->rebuild ? 1.f : 0.f;
-    out[1] = s[0][0]; out[2] = s[0][1]; out[3] = s[0][2]; out[4] = s[0][3];
-    out[5] = out[6] = out[7] = 0.f;
+    for (int k = 0; k < 4; k++) partial[4 * blockIdx.x + k] = s[0][k];
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
+  __syncthreads();
+  if (!last || threadIdx.x != 0) return;
+  __threadfence();
+  rlo = INFINITY; rhi = -INFINITY; ext = 0.f; pad = 0.f;
+  for (int b = 0; b < (int)gridDim.x; b++) {
+    const volatile float *p = partial + 4 * b;
+    rlo = fminf(rlo, p[0]); rhi = fmaxf(rhi, p[1]); ext = fmaxf(ext, p[2]); pad = fmaxf(pad, p[3]);
+  }
+  *ticket = 0u;
+  out[0] = st->rebuild ? 1.f : 0.f;
+  out[1] = rlo; out[2] = rhi; out[3] = ext; out[4] = pad;
+  out[5] = out[6] = out[7] = 0.f;
 }
 
 // does [lo-m, hi+m] reach region [qlo, qhi] under the periodic image that brings them closest?
@@ -214,24 +233,45 @@ int shard_exchange(dpm3d_ctx *h, int pbc, float L) {
   Nccl &N = nccl();
   ncclComm_t comm = static_cast<ncclComm_t>(h->comm);
   float4 *pos = h->pos[h->cur], *bnd = h->bnd[h->cur];
-  shard_prepare_kernel<<<1, 256, 0, h->stream>>>(bnd, h->nc, h->st, h->gather_send,
-                                                 h->att_active ? ATT_REACH / RANGE_HEADROOM * 1.0001f : 0.0f);
+  // DPM_TRACE: device time of each phase of ONE exchange (the 400th of the process), events on the stream
+  static const bool trace = getenv("DPM_TRACE") != nullptr;
+  static int ncall = 0;
+  const bool tr = trace && ++ncall == 400;
+  cudaEvent_t tev[7] = {};
+  auto mark = [&](int i) { if (tr) { cudaEventCreate(&tev[i]); cudaEventRecord(tev[i], h->stream); } };
+  mark(0);
+  shard_prepare_kernel<<<PREP_CTAS, 256, 0, h->stream>>>(bnd, h->nc, h->st, h->gather_send,
+                                                         h->att_active ? ATT_REACH / RANGE_HEADROOM * 1.0001f : 0.0f, h->prep_partial, h->prep_ticket);
+  mark(1);
   DPM_NCCL_TRY(N.AllGather(h->gather_send, h->gather_all, GATHER, ncclFloat, comm, h->stream));
+  mark(2);
   shard_select_kernel<<<1, 256, 0, h->stream>>>(bnd, h->nc, h->st, h->sd, h->gather_all, h->rank, h->nranks, h->npeers, h->peer[0],
                                                  h->npeers > 1 ? h->peer[1] : -1, h->sendlist[0], h->sendlist[1], h->ghost_cap,
                                                  h->skin_rel, pbc, L);
+  mark(3);
   shard_pack_kernel<<<h->ghost_cap * h->npeers, 128, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->sendlist[0], h->sendlist[1],
                                                                       h->sendbuf[0], h->sendbuf[1], h->ghost_cap, h->nv);
   DPM_CUDA_TRY(cudaGetLastError());
+  mark(4);
   DPM_NCCL_TRY(N.GroupStart());
   for (int p = 0; p < h->npeers; p++) {
     DPM_NCCL_TRY(N.Send(h->sendbuf[p], h->msg_bytes, ncclChar, h->peer[p], comm, h->stream));
     DPM_NCCL_TRY(N.Recv(h->recvbuf[p], h->msg_bytes, ncclChar, h->peer[p], comm, h->stream));
   }
   DPM_NCCL_TRY(N.GroupEnd());
+  mark(5);
   shard_unpack_kernel<<<h->ghost_cap * h->npeers, 128, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->recvbuf[0], h->recvbuf[1], h->npeers,
                                                                         h->nc, h->ghost_cap, h->nv);
   DPM_CUDA_TRY(cudaGetLastError());
+  mark(6);
+  if (tr) {
+    cudaEventSynchronize(tev[6]);
+    float t[6];
+    for (int i = 0; i < 6; i++) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
+    fprintf(stderr, "[dpm3d] rank %d halo exchange (us): prepare %.1f  allgather %.1f  select %.1f  pack %.1f  send/recv %.1f  unpack %.1f  total %.1f\n",
+            h->rank, t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f, t[4] * 1e3f, t[5] * 1e3f, (t[0] + t[1] + t[2] + t[3] + t[4] + t[5]) * 1e3f);
+    for (auto &e : tev) cudaEventDestroy(e);
+  }
   h->stats.launches += 4;
   h->stats.halo_bytes += (uint64_t)h->msg_bytes * h->npeers;
   return DPM_OK;
@@ -247,7 +287,7 @@ int shard_check(dpm3d_ctx *h) {
 }
 
 void shard_free(dpm3d_ctx *h) {
-  void *ptrs[] = {h->gid, h->sd, h->gather_send, h->gather_all, h->sendbuf[0], h->sendbuf[1], h->recvbuf[0], h->recvbuf[1],
+  void *ptrs[] = {h->prep_partial, h->prep_ticket, h->gid, h->sd, h->gather_send, h->gather_all, h->sendbuf[0], h->sendbuf[1], h->recvbuf[0], h->recvbuf[1],
                   h->sendlist[0], h->sendlist[1]};
   for (void *p : ptrs) if (p) cudaFree(p);
   h->gid = nullptr; h->sd = nullptr;
@@ -309,6 +349,9 @@ int dpm3d_shard_init(dpm3d_t *h, int rank, int nranks, const uint8_t id[128], in
   DPM_CUDA_TRY(cudaMalloc(&h->sd, sizeof(ShardDev)));
   DPM_CUDA_TRY(cudaMemset(h->sd, 0, sizeof(ShardDev)));
   DPM_CUDA_TRY(cudaMalloc(&h->gather_send, sizeof(float) * GATHER));
+  DPM_CUDA_TRY(cudaMalloc(&h->prep_partial, sizeof(float) * 4 * PREP_CTAS));
+  DPM_CUDA_TRY(cudaMalloc(&h->prep_ticket, sizeof(unsigned)));
+  DPM_CUDA_TRY(cudaMemset(h->prep_ticket, 0, sizeof(unsigned)));
   DPM_CUDA_TRY(cudaMalloc(&h->gather_all, sizeof(float) * GATHER * nranks));
   for (int p = 0; p < h->npeers; p++) {
     DPM_CUDA_TRY(cudaMalloc(&h->sendbuf[p], h->msg_bytes));
