@@ -349,4 +349,4 @@ def test_threaded_pack_unpack_equals_flat_path():
     h.euler_update(V, *[P[k] for k in PKEYS], 4, 0.01, 25.0, 0.0, d["PBC"], float(d["L"]), forces_out=F)
     h.close()
     assert np.array_equal(Vc, V[:, :3]) and np.array_equal(Fc, F[:, :3])
-    assert abs(out[5].GetVolume() - 4.0) < 0.5
+    assert 0.5 < out[5].GetVolume() < 4.2 and out[5].GetVolume() == T.Cells[5].GetVolume()  # unpack refreshed the cell
