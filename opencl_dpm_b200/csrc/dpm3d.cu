@@ -300,7 +300,12 @@ int dpm3d_create(dpm3d_t **out, int device, int ncells, int nv, int nf, const ui
   {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    h->contact_grid = sms * 8;
+    // the contact kernel is grid-stride over the unit queue: exactly the CTAs that are resident at once (no second wave)
+    int per = 0;
+    const char *cg = getenv("DPM_CONTACT_CTAS_PER_SM");  // experiments
+    if (cg) per = atoi(cg);
+    else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, dpm3d_contact_kernel<false>, CONTACT_THREADS, 0) != cudaSuccess) per = 0;
+    h->contact_grid = sms * (per > 0 ? per : 8);
   }
   h->smem = smem_for(h);
   TRYB(set_smem(h));
