@@ -74,7 +74,8 @@ struct NbrBuffers {
   int *ext_list;  // far2d: [nc] scratch, the cells near the global extremes (filled by the rebuild kernel)
 };
 
-// Launches the cooperative rebuild kernel (no-op on the device when st->rebuild == 0).
+// Launches the rebuild kernel as one thread-block cluster, with programmatic dependent launch (no-op on the device when
+// st->rebuild == 0); coop_grid = rebuild_max_grid(): the CTAs of that cluster (sizes of NbrBuffers::partial / chunk_sum).
 cudaError_t launch_rebuild(const NbrBuffers &nb, cudaStream_t stream, int coop_grid);
 int rebuild_max_grid(int device);
 

@@ -80,7 +80,7 @@ __device__ __forceinline__ int axis_bin(const dpm_grid_t &g, int d, int pbc, flo
   return b;
 }
 // bin coordinates of a cell; axes >= nd stay 0.  (No dynamically indexed local arrays in this file: with them
-// nvcc 12.9 -O3 produced overlapping stack slots in the cooperative kernel below.)
+// nvcc 12.9 -O3 produced overlapping stack slots in the rebuild kernel below.)
 __device__ __forceinline__ int3 cell_bin3(const dpm_grid_t &g, int nd, int pbc, float L, const float4 lo, const float4 hi) {
   int3 ib = make_int3(0, 0, 0);
   ib.x = axis_bin(g, 0, pbc, L, lo.x, hi.x);
