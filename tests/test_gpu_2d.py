@@ -197,3 +197,31 @@ def test_step_resident_equals_repeated_cleulerupdate_2d():
         B.StepResident(20, 0.005)
     B.SyncCells()
     assert np.array_equal(H.flat2d(A)["verts"], H.flat2d(B)["verts"])
+
+
+@pytest.mark.parametrize("nx,pbc", [(2, 1), (3, 1), (4, 0), (6, 1)])
+def test_attraction_and_repulsion_in_small_and_open_boxes(nx, pbc):
+    """The attraction's near-vertex compaction and the per-vertex culls are only applied when the periodic box is large
+    against the cells (`att_cull_ok` / `own_cull_ok`, dpm2d.cu); 2 x 2 and 3 x 3 cells in a box of two / three lattice
+    spacings take the no-cull paths (every image is within reach), an open box has no images at all.  All against the
+    all-pairs oracle, 5 steps, each re-seeded from the oracle state."""
+    from opencl_dpm_b200 import synth
+
+    O = _oracle()
+    d = synth.tissue2d(nx, nv=32, Kat=0.7)
+    d["PBC"] = pbc
+    h = _handle(d, skin_rel=0.1, max_candidates=64)
+    V = d["verts"].copy()
+    worst = 0.0
+    for s in range(5):
+        V1, F = _gpu(h, d, V)
+        Fr = O.forces2d(V, d["nv"], *[d[k] for k in PK], d["Kre"], d["Kat"], d["PBC"], d["L"])
+        tol = H.force_tol(Fr)
+        err = float(np.abs(F - Fr).max())
+        worst = max(worst, err / tol)
+        assert err <= tol, f"step {s}: force error {err:.3e} > {tol:.3e}"
+        V = V + Fr * d["dt"]
+    Fatt = O.forces2d(d["verts"], d["nv"], *[d[k] for k in PK], d["Kre"], d["Kat"], d["PBC"], d["L"], which=8)
+    assert np.abs(Fatt).max() > 1e-3  # the attraction is active in this fixture
+    print(f"nx={nx} pbc={pbc}: worst error/tol {worst:.2f}")
+    h.close()
