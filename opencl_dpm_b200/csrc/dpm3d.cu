@@ -389,7 +389,7 @@ static int upload_common(dpm3d_t *h, const float *verts4, bool on_device, const 
   dpm3d_bounds_kernel<<<h->nc, STEP_THREADS, h->smem, h->stream>>>(h->pos[0], h->bnd[0], h->flag[0], h->nc, cell_topo(h), h->cellB);
   DPM_CUDA_TRY(cudaGetLastError());
   h->stats.launches += 1;
-  h->stats.steps = 0; h->stats.rebuilds = 0; h->stats.contact_evals = 0;  // per-upload counters (launches stay cumulative)
+  h->stats.steps = 0; h->stats.rebuilds = 0; h->stats.contact_evals = 0; h->stats.halo_bytes = 0;  // per-upload counters (launches stay cumulative)
   // mark the neighbour lists stale
   static const int one = 1;
   DPM_CUDA_TRY(cudaMemcpyAsync(&h->st->rebuild, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
