@@ -280,3 +280,26 @@ def test_threaded_pack_keeps_the_reference_validation_errors():
     T.Cells = cells
     with pytest.raises(RuntimeError, match="Invalid spring constants"):
         T.CLEulerUpdate(1, 0.01)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's all-pairs algorithm on the host cores, oracle port): one JSON line on
+    stdout with the keys the driver reads; non-zero ranks print nothing and exit 0."""
+    import json
+    import subprocess
+    import sys
+
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C162", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [x for x in r.stdout.splitlines() if x.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "vertex-steps/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"] == {"value": d["value"], "unit": "vertex-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["name"] == "C162"
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True, text=True,
+                        timeout=60, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
