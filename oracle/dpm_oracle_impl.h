@@ -293,6 +293,39 @@ void FN(oracle3d_forces_range)(int nc, int nv, int nf, const uint32_t *faces, co
                      c0, c1, -1, NULL);
 }
 
+/* RepellingForces (shaders/Cell3D_Kernel.cl:251-310) for vertices [vi0, vi1) of cell ci against ALL nc cells present
+ * (the reference's all-pairs loop over cj, :269-309), nothing else: a bounded sample of the reference algorithm for
+ * tissues where even one cell's all-pairs work takes minutes (bench.py --impl reference).  The cj loop is split in
+ * NCHUNK chunks so that a handful of vertices still occupies every host thread; a vertex's partial forces are added
+ * in chunk order.  out: (vi1 - vi0) x 4. */
+void FN(oracle3d_repel_sample)(int nc, int nv, int nf, const uint32_t *faces, const REAL *verts, REAL Kc, int PBC, REAL L,
+                               int ci, int vi0, int vi1, REAL *out) {
+  enum { NCHUNK = 64 };
+  const int nvs = vi1 - vi0;
+  REAL *coms = (REAL *)malloc(sizeof(REAL) * 3 * (size_t)nc);
+  REAL *part = (REAL *)calloc((size_t)nvs * NCHUNK * 3, sizeof(REAL));
+#pragma omp parallel for schedule(static)
+  for (int c = 0; c < nc; c++) FN(com3d)(verts + 4 * (size_t)c * nv, nv, coms + 3 * c);
+#pragma omp parallel for collapse(2) schedule(dynamic, 1)
+  for (int s = 0; s < nvs; s++) {
+    for (int ch = 0; ch < NCHUNK; ch++) {
+      const REAL *p = verts + 4 * ((size_t)ci * nv + vi0 + s);
+      REAL *fo = part + 3 * ((size_t)s * NCHUNK + ch);
+      const int j0 = (int)((long long)nc * ch / NCHUNK), j1 = (int)((long long)nc * (ch + 1) / NCHUNK);
+      for (int cj = j0; cj < j1; cj++) {
+        if (cj == ci) continue;
+        FN(repel_pair3d)(verts + 4 * (size_t)cj * nv, faces, nf, coms + 3 * ci, coms + 3 * cj, PBC, L, Kc, p, fo);
+      }
+    }
+  }
+  for (int s = 0; s < nvs; s++) {
+    REAL f[3] = {0, 0, 0};
+    for (int ch = 0; ch < NCHUNK; ch++) for (int d = 0; d < 3; d++) f[d] += part[3 * ((size_t)s * NCHUNK + ch) + d];
+    out[4 * s] = f[0]; out[4 * s + 1] = f[1]; out[4 * s + 2] = f[2]; out[4 * s + 3] = 0;
+  }
+  free(coms); free(part);
+}
+
 /* shaders/Cell3D_Kernel.cl:313-364  AllVertAttraction, literally (scatter form: the work-item of vertex (ci,vi)
  * visits every vertex (cj,vj) of every other cell and adds -t to its own force and +t to the OTHER vertex's force,
  * with the rest length l0[ci] of ITS cell).  The reference host never enqueues this kernel, so the
@@ -390,10 +423,10 @@ static int FN(inside2d)(const REAL *p, const REAL *Vj, int nj, int PBC, REAL L) 
  * Kernel order src/Tissue2D.cpp:216-221.  cand==NULL => all-pairs. For the culled form
  * cand lists candidate cells for attraction+repulsion (near set) and far_count/far lists
  * the cells whose |d|>L wrap quirk can fire; per-vertex culls applied inside. */
-void FN(oracle2d_forces)(int nc, int S, const int32_t *NV, const REAL *verts, REAL *forces, const REAL *Ka,
+static void FN(forces2d_range)(int nc, int S, const int32_t *NV, const REAL *verts, REAL *forces, const REAL *Ka,
                          const REAL *Kl, const REAL *Kb, const REAL *a0, const REAL *l0, const REAL *r0, REAL Kre,
                          REAL Kat, int PBC, REAL L, int which, const int32_t *cand_count, const int32_t *cand,
-                         int cand_stride, int32_t *inside_flags) {
+                         int cand_stride, int32_t *inside_flags, int c0, int c1) {
   memset(forces, 0, sizeof(REAL) * 2 * (size_t)nc * S);
   REAL *lo = (REAL *)malloc(sizeof(REAL) * 2 * nc), *hi = (REAL *)malloc(sizeof(REAL) * 2 * nc);
   for (int ci = 0; ci < nc; ci++) {
@@ -406,7 +439,7 @@ void FN(oracle2d_forces)(int nc, int S, const int32_t *NV, const REAL *verts, RE
     }
   }
 #pragma omp parallel for schedule(dynamic, 1)
-  for (int ci = 0; ci < nc; ci++) {
+  for (int ci = c0; ci < c1; ci++) {
     const int n = NV[ci];
     const REAL *V = verts + 2 * (size_t)ci * S;
     REAL *Fo = forces + 2 * (size_t)ci * S;
@@ -505,6 +538,21 @@ void FN(oracle2d_forces)(int nc, int S, const int32_t *NV, const REAL *verts, RE
     }
   }
   free(lo); free(hi);
+}
+
+void FN(oracle2d_forces)(int nc, int S, const int32_t *NV, const REAL *verts, REAL *forces, const REAL *Ka,
+                         const REAL *Kl, const REAL *Kb, const REAL *a0, const REAL *l0, const REAL *r0, REAL Kre,
+                         REAL Kat, int PBC, REAL L, int which, const int32_t *cand_count, const int32_t *cand,
+                         int cand_stride, int32_t *inside_flags) {
+  FN(forces2d_range)(nc, S, NV, verts, forces, Ka, Kl, Kb, a0, l0, r0, Kre, Kat, PBC, L, which, cand_count, cand, cand_stride,
+                     inside_flags, 0, nc);
+}
+
+/* Same, all-pairs, forces of cells [c0, c1) only (against ALL cells): a bounded sample of the reference algorithm. */
+void FN(oracle2d_forces_range)(int nc, int S, const int32_t *NV, const REAL *verts, REAL *forces, const REAL *Ka,
+                               const REAL *Kl, const REAL *Kb, const REAL *a0, const REAL *l0, const REAL *r0, REAL Kre,
+                               REAL Kat, int PBC, REAL L, int which, int c0, int c1) {
+  FN(forces2d_range)(nc, S, NV, verts, forces, Ka, Kl, Kb, a0, l0, r0, Kre, Kat, PBC, L, which, NULL, NULL, 0, NULL, c0, c1);
 }
 
 /* EulerUpdate :270-281 (real vertices only; forces are NOT zeroed here so the

@@ -89,6 +89,20 @@ def forces3d_range(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, c0, c1, wh
     return Fo
 
 
+def repel_sample3d(verts4, faces, nc, Kc, PBC, L, ci, vi0, vi1):
+    """All-pairs RepellingForces (fp32) of vertices [vi0, vi1) of cell ci against all nc cells in verts4 — the bounded
+    sample of the reference algorithm that bench.py --impl reference times.  Returns [(vi1-vi0), 4]."""
+    faces = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+    V = np.ascontiguousarray(verts4, dtype=np.float32).reshape(-1, 4)
+    nv = V.shape[0] // nc
+    out = np.zeros((vi1 - vi0, 4), np.float32)
+    fn = lib().oracle3d_repel_sample_f32
+    fn.restype = None
+    fn(int(nc), int(nv), faces.shape[0], _p(faces, C.c_uint32), _p(V, C.c_float), C.c_float(Kc), int(PBC), C.c_float(L),
+       int(ci), int(vi0), int(vi1), _p(out, C.c_float))
+    return out
+
+
 def run3d(verts4, faces, Kv, Ka, Ks, v0, a0, l0, Kc, PBC, L, nsteps, dt, which=15, dtype=np.float32, stale_from=-1):
     """nsteps of the all-pairs reference algorithm. Returns (verts4, last_forces4).
     stale_from >= 0: emulate the reference's volume race as it resolves on NVIDIA OpenCL (faces >= stale_from use
@@ -191,6 +205,20 @@ def forces2d(verts2, NV, Ka, Kl, Kb, a0, l0, r0, Kre, Kat, PBC, L, which=31, can
        int(which), _p(None if cand_count is None else np.ascontiguousarray(cand_count, np.int32), C.c_int32),
        _p(None if cand is None else np.ascontiguousarray(cand, np.int32), C.c_int32), int(K), _p(inside, C.c_int32))
     return (Fo, inside) if want_inside else Fo
+
+
+def forces2d_range(verts2, NV, Ka, Kl, Kb, a0, l0, r0, Kre, Kat, PBC, L, c0, c1, which=31):
+    """All-pairs 2D forces (fp32) of cells [c0, c1) only — a bounded sample of the reference algorithm."""
+    V = np.ascontiguousarray(verts2, dtype=np.float32)
+    nc, S = V.shape[0], V.shape[1]
+    NV = _arr(NV, nc, np.int32)
+    Fo = np.zeros_like(V)
+    P = [_arr(x, nc, np.float32) for x in (Ka, Kl, Kb, a0, l0, r0)]
+    fn = lib().oracle2d_forces_range_f32
+    fn.restype = None
+    fn(nc, S, _p(NV, C.c_int32), _p(V, C.c_float), _p(Fo, C.c_float), *[_p(x, C.c_float) for x in P], C.c_float(Kre),
+       C.c_float(Kat), int(PBC), C.c_float(L), int(which), int(c0), int(c1))
+    return Fo
 
 
 def run2d(verts2, NV, Ka, Kl, Kb, a0, l0, r0, Kre, Kat, PBC, L, nsteps, dt, which=31, dtype=np.float32):

@@ -290,7 +290,7 @@ def test_bench_reference_arm_contract():
     import sys
 
     env = dict(os.environ, RANK="0", WORLD_SIZE="1")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C162", "--steps", "1", "--warmup", "0"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C162", "--steps", "1", "--warmup", "0", "--no-opencl"],
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [x for x in r.stdout.splitlines() if x.strip()]
@@ -300,6 +300,28 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": "vertex-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["name"] == "C162"
+    assert d["cpu_baseline_culled"]["value"] > d["value"] and d["cpu_baseline_culled"]["kind"] == "port"
+    # the CPU arm never maps the product library: its tissue comes from the oracle's own geometry helpers
+    assert d["native_so_loaded"] is not None and all(x.startswith("oracle/") for x in d["native_so_loaded"]), d["native_so_loaded"]
+    assert d["gpu_launches"] == 0
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True, text=True,
                         timeout=60, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_bench_reference_arm_is_bounded_on_config_e():
+    """Config E (262,144 cells) is the default workload of the N > 1 runs: the CPU arm must answer in about a minute (round 1
+    timed out there), from a bounded block of the lattice scaled to the whole tissue, and only on rank 0."""
+    import json
+    import subprocess
+    import sys
+    import time
+
+    t0 = time.time()
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "8", "--workload", "E162", "--steps", "1",
+                        "--warmup", "0", "--no-opencl"], capture_output=True, text=True, timeout=240,
+                       env=dict(os.environ, RANK="0", WORLD_SIZE="8"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip())
+    assert d["impl"] == "reference" and d["config"]["name"] == "E162" and d["n_gpus"] == 8 and d["value"] > 0
+    assert "scaled" in d["cpu_baseline"]["sample"] and time.time() - t0 < 200
