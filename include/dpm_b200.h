@@ -111,6 +111,9 @@ int dpm3d_set_stream(dpm3d_t *h, void *cuda_stream);
 /* skin_rel: Verlet skin as a fraction of the largest cell extent (default 0.1);
  * max_candidates: per-cell candidate-list capacity K (default 32). Takes effect at the next upload. */
 int dpm3d_set_neighbor_params(dpm3d_t *h, float skin_rel, int max_candidates);
+/* The values in force: dpm3d_euler_update doubles max_candidates when a candidate list overflows, so a caller that
+ * sizes the `cand` buffer of dpm3d_get_neighbor_artifacts must ask for the current K first. */
+int dpm3d_get_neighbor_params(dpm3d_t *h, float *skin_rel, int *max_candidates);
 int dpm3d_set_force_mask(dpm3d_t *h, unsigned mask);
 /* Reference-race compatibility (off by default).  VolumeForceUpdate writes cellVolumes[ci] from work-item fi==0
  * and reads it back behind a work-group-scoped barrier (shaders/Cell3D_Kernel.cl:74-83) while the launch leaves
@@ -130,7 +133,9 @@ int dpm3d_upload_device(dpm3d_t *h, const float *verts4_dev, const float *Kv, co
                         const float *v0, const float *a0, const float *l0);
 /* nsteps of {ClearForces, Volume, SurfaceArea, StickToSurface, Repelling, EulerPosition}
  * (src/Tissue3D.cpp:372-423) fused; asynchronous.  Kat is only used when the force mask contains DPM3D_ATTRACT
- * (the reference never launches AllVertAttraction, SURVEY F12: by default Kat has no effect, as in the reference). */
+ * (the reference never launches AllVertAttraction, SURVEY F12: by default Kat has no effect, as in the reference).
+ * Every 1000 timesteps the call synchronises and checks the device-side error flags, as the reference drains its
+ * queue "to catch errors early" (src/Tissue3D.cpp:437-444): a capacity overflow is reported then, not nsteps later. */
 int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, float L);
 int dpm3d_sync(dpm3d_t *h);
 /* verts4 and/or forces4 may be NULL. forces4 = forces of the last executed step. */
@@ -177,6 +182,7 @@ int dpm2d_create(dpm2d_t **h, int device, int ncells, int max_nv);
 int dpm2d_destroy(dpm2d_t *h);
 int dpm2d_set_stream(dpm2d_t *h, void *cuda_stream);
 int dpm2d_set_neighbor_params(dpm2d_t *h, float skin_rel, int max_candidates);
+int dpm2d_get_neighbor_params(dpm2d_t *h, float *skin_rel, int *max_candidates);
 int dpm2d_set_force_mask(dpm2d_t *h, unsigned mask);
 /* verts2: ncells*max_nv*2 floats padded as the reference pads (src/Tissue2D.cpp:139);
  * nv: vertices per cell; Ka,Kl,Kb,a0,l0,r0 per cell (src/Tissue2D.cpp:129-136). */

@@ -185,8 +185,16 @@ class Dpm3D:
     def rebuild_neighbors(self, pbc: int, L: float):
         _check(lib().dpm3d_rebuild_neighbors(self._h, int(pbc), C.c_float(L)))
 
+    def neighbor_params(self):
+        """(skin_rel, max_candidates) in force — euler_update may have grown K after a candidate-list overflow"""
+        s, k = C.c_float(0), C.c_int(0)
+        _check(lib().dpm3d_get_neighbor_params(self._h, C.byref(s), C.byref(k)))
+        self.K = k.value
+        return s.value, k.value
+
     def neighbor_artifacts(self):
         g = Grid()
+        self.neighbor_params()  # the library's current K sizes `cand` (never a stale Python-side copy)
         _check(lib().dpm3d_get_neighbor_artifacts(self._h, C.byref(g), None, None, None, None, None))
         bin_id = np.empty(self.nc, np.int32); order = np.empty(self.nc, np.int32)
         bin_start = np.empty(g.nbins + 1, np.int32); cc = np.empty(self.nc, np.int32)
@@ -273,8 +281,15 @@ class Dpm2D:
     def rebuild_neighbors(self, Kat, pbc, L):
         _check(lib().dpm2d_rebuild_neighbors(self._h, C.c_float(Kat), int(pbc), C.c_float(L)))
 
+    def neighbor_params(self):
+        s, k = C.c_float(0), C.c_int(0)
+        _check(lib().dpm2d_get_neighbor_params(self._h, C.byref(s), C.byref(k)))
+        self.K = k.value
+        return s.value, k.value
+
     def neighbor_artifacts(self):
         g = Grid()
+        self.neighbor_params()  # the library's current K sizes `cand`
         _check(lib().dpm2d_get_neighbor_artifacts(self._h, C.byref(g), None, None, None, None, None))
         bin_id = np.empty(self.nc, np.int32); order = np.empty(self.nc, np.int32)
         bin_start = np.empty(g.nbins + 1, np.int32); cc = np.empty(self.nc, np.int32)

@@ -497,6 +497,13 @@ int dpm2d_set_neighbor_params(dpm2d_t *h, float skin_rel, int max_candidates) {
   return DPM_OK;
 }
 
+int dpm2d_get_neighbor_params(dpm2d_t *h, float *skin_rel, int *max_candidates) {
+  if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
+  if (skin_rel) *skin_rel = h->skin_rel;
+  if (max_candidates) *max_candidates = h->K;
+  return DPM_OK;
+}
+
 int dpm2d_set_force_mask(dpm2d_t *h, unsigned mask) {
   if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
   h->mask = mask & DPM2D_ALL;
@@ -576,6 +583,10 @@ int dpm2d_step(dpm2d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
       DPM_CUDA_TRY(cudaLaunchKernelEx(&cfg, dpm2d_step_kernel, p));
     }
     h->cur ^= 1;
+    if ((s + 1) % 1000 == 0 && s + 1 < nsteps) {  // catch a capacity overflow early (the 3D reference drains its queue every 1000 steps)
+      int rc = check_flags2(h);
+      if (rc) return rc;
+    }
   }
   h->stats.steps += (uint64_t)nsteps;
   h->stats.launches += 2ull * (uint64_t)nsteps;

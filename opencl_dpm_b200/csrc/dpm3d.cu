@@ -353,6 +353,13 @@ int dpm3d_set_neighbor_params(dpm3d_t *h, float skin_rel, int max_candidates) {
   return DPM_OK;
 }
 
+int dpm3d_get_neighbor_params(dpm3d_t *h, float *skin_rel, int *max_candidates) {
+  if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
+  if (skin_rel) *skin_rel = h->skin_rel;
+  if (max_candidates) *max_candidates = h->K;
+  return DPM_OK;
+}
+
 int dpm3d_set_compat(dpm3d_t *h, int stale_volume_from_face) {
   if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
   h->stale_from = stale_volume_from_face < 0 ? -1 : stale_volume_from_face;
@@ -421,10 +428,12 @@ int dpm3d_rebuild_neighbors(dpm3d_t *h, int pbc, float L) {
   return DPM_OK;
 }
 
+static int check_device_flags(dpm3d_t *h);
+
 int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, float L) {
+  if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
   // AllVertAttraction is never enqueued by the reference host: Kat only acts under DPM3D_ATTRACT
   const bool attract = (h->mask & DPM3D_ATTRACT) && Kat != 0.0f;  // the kernel returns at once when Kat == 0 (:318-319)
-  if (!h) return fail(DPM_ERR_INVALID_ARGUMENT, "NULL handle");
   if (nsteps <= 0) return fail(DPM_ERR_INVALID_ARGUMENT, "nsteps must be positive");                          // src/Tissue3D.cpp:123-126
   if (!(dt > 0.0f) || dt > 0.1f) return fail(DPM_ERR_INVALID_ARGUMENT, "dt must be positive and reasonable");  // :127-131
   if (!h->uploaded) return fail(DPM_ERR_INVALID_ARGUMENT, "dpm3d_step before dpm3d_upload");
@@ -476,6 +485,10 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
     DPM_CUDA_TRY(launch_step(h, p));
     if (tr) cudaEventRecord(tev[4], h->stream);
     h->cur ^= 1;
+    if ((s + 1) % 1000 == 0 && s + 1 < nsteps) {  // the reference drains its queue every 1000 steps "to catch errors early" (:437-444)
+      int rc = check_device_flags(h);
+      if (rc) return rc;
+    }
   }
   if (traced >= 0) {
     cudaEventSynchronize(tev[4]);
