@@ -368,7 +368,7 @@ class Runner:
 
     def stats_dict(self):
         st = self.h.stats()
-        return {"steps": int(st.steps), "rebuilds": int(st.rebuilds), "contact_evals": int(st.contact_evals), "literal": int(st.reserved[0]),
+        return {"steps": int(st.steps), "rebuilds": int(st.rebuilds), "contact_evals": int(st.contact_evals), "literal": int(st.reserved[0]), "nonstar": int(st.reserved[1] & 0xffffffff),
                 "halo_bytes": int(st.halo_bytes), "launches": int(st.launches)}
 
     def timed_windows(self, batch, inner, steps, warmup, flush, barrier=None):
@@ -427,6 +427,7 @@ def trajectory(R, phases, peak):
                     "roofline_frac": vs * R.balg / 1e9 / peak,
                     "contact_evals_per_timestep": (st["contact_evals"] - prev["contact_evals"]) / n,
                     "literal_fallback_evals_per_timestep": (st["literal"] - prev["literal"]) / n,
+                    "nonstar_evals_per_timestep": (st["nonstar"] - prev["nonstar"]) / n,
                     "rebuilds": st["rebuilds"] - prev["rebuilds"]})
         prev, s0, t_total = st, s1, t_total + ms
     vs = R.nvert * phases[-1] / (t_total * 1e-3)
@@ -450,7 +451,8 @@ def short_line(name, local, stream, flush, peak, equilibrate, inner=25, steps=3,
     return {"name": name, "workload": d["desc"], "vertices": R.nvert, "value": vs, "unit": "vertex-steps/s", "ms_per_timestep": ms / n,
             "roofline_frac": vs * R.balg / 1e9 / peak, "timesteps_per_step": inner, "steps": steps, "equilibrate": equilibrate,
             "contact_evals_per_timestep": st["contact_evals"] / max(1, st["steps"]),
-            "literal_fallback_evals_per_timestep": st["literal"] / max(1, st["steps"])}
+            "literal_fallback_evals_per_timestep": st["literal"] / max(1, st["steps"]),
+            "nonstar_evals_per_timestep": st["nonstar"] / max(1, st["steps"])}
 
 
 def e2e_host_classes(batch_host, d, inner, steps):
@@ -725,7 +727,8 @@ def main():
                          "traffic_source": traffic_src, "algorithmic_bytes_per_vertex_step": balg, "us_per_launch": t_launch * 1e6},
             "stats": {"rebuilds": st["rebuilds"], "contact_evals_per_timestep": st["contact_evals"] / max(1, st["steps"]),
                       "wall_s_timed_region": t_wall, "halo_bytes_per_timestep_rank0": st["halo_bytes"] / max(1, st["steps"]),
-                      "literal_fallback_evals_per_timestep": st["literal"] / max(1, st["steps"])},
+                      "literal_fallback_evals_per_timestep": st["literal"] / max(1, st["steps"]),
+                      "nonstar_evals_per_timestep": st["nonstar"] / max(1, st["steps"])},
             **extras,
             "native_so_loaded": native_so_loaded(),
         }

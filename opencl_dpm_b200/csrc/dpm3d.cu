@@ -295,6 +295,8 @@ int dpm3d_create(dpm3d_t **out, int device, int ncells, int nv, int nf, const ui
   TRYB(cudaMalloc(&h->unit_base, sizeof(int) * ncells));
   TRYB(cudaMalloc(&h->unit_cnt, sizeof(int) * ncells));
   TRYB(cudaMemset(h->unit_cnt, 0, sizeof(int) * ncells));
+  h->npatch = (nf + PATCH_F - 1) / PATCH_F;
+  TRYB(cudaMalloc(&h->patch_box, sizeof(float4) * 2 * (size_t)h->npatch * ncells));
   rc = alloc_units(h, std::min(4096, std::max(256, 4 * nv)));
   if (rc) return bail(rc);
   {
@@ -321,7 +323,7 @@ int dpm3d_destroy(dpm3d_t *h) {
   shard_free(h);
   void *ptrs[] = {h->pos[0], h->pos[1], h->force, h->bnd[0], h->bnd[1], h->cellA, h->cellB, h->faces, h->ring_nbr, h->ring_face,
                   h->valence, h->face_adj, h->ring_tab, h->ring_end, h->dir_table, h->st, h->bbox_lo, h->bbox_hi, h->bin_id, h->order, h->bin_count, h->bin_start, h->cand_count,
-                  h->cand, h->partial, h->chunk_sum, h->unit_rec, h->unit_w, h->unit_att, h->unit_base, h->unit_cnt, h->flag[0], h->flag[1], h->vlist, h->vlist_cnt};
+                  h->cand, h->partial, h->chunk_sum, h->unit_rec, h->unit_w, h->unit_att, h->unit_base, h->unit_cnt, h->flag[0], h->flag[1], h->vlist, h->vlist_cnt, h->patch_box};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (h->h_cell) cudaFreeHost(h->h_cell);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -445,6 +447,9 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
   p.cand_count = h->cand_count; p.cand = h->cand; p.K = h->K;
   p.bbox_lo = h->bbox_lo; p.bbox_hi = h->bbox_hi; p.st = h->st;
   p.vlist = h->vlist; p.vlist_cnt = h->vlist_cnt;
+  p.patch_box = h->patch_box; p.npatch = h->npatch;
+  p.n_total_dev = h->nranks > 1 ? reinterpret_cast<const int *>(h->sd) : nullptr;  // ShardDev::n_total is its first member
+  const int units_grid = h->nranks > 1 ? h->nslots : h->nc;  // sharded: ghost cells refresh their patch boxes too
   p.unit_rec = h->unit_rec; p.unit_w = h->unit_w; p.unit_att = h->unit_att; p.unit_base = h->unit_base; p.unit_cnt = h->unit_cnt; p.unit_cap = h->unit_cap;
   const bool repel = (h->mask & DPM3D_REPEL) && Kre != 0.0f;
   p.nc = h->nc; p.nv = h->nv; p.nf = h->nf; p.dt = dt; p.Kc = Kre; p.pbc = pbc; p.L = L;
@@ -475,8 +480,8 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
     p.flag_in = h->flag[h->cur]; p.flag_out = h->flag[h->cur ^ 1];
     p.force_out = (s == nsteps - 1) ? h->force : nullptr;  // forces are only read back after the last step (:425-434)
     if (repel || attract) {
-      DPM_CUDA_TRY(attract ? launch_pdl(dpm3d_units_kernel<true>, h->nc, UNITS_THREADS, 0, h->stream, p)
-                           : launch_pdl(dpm3d_units_kernel<false>, h->nc, UNITS_THREADS, 0, h->stream, p));
+      DPM_CUDA_TRY(attract ? launch_pdl(dpm3d_units_kernel<true>, units_grid, UNITS_THREADS, 0, h->stream, p)
+                           : launch_pdl(dpm3d_units_kernel<false>, units_grid, UNITS_THREADS, 0, h->stream, p));
       if (tr) cudaEventRecord(tev[2], h->stream);
       DPM_CUDA_TRY(attract ? launch_pdl(dpm3d_contact_kernel<true>, h->contact_grid, CONTACT_THREADS, 0, h->stream, p)
                            : launch_pdl(dpm3d_contact_kernel<false>, h->contact_grid, CONTACT_THREADS, 0, h->stream, p));

@@ -36,6 +36,8 @@ struct dpm3d_ctx {
   int *unit_base = nullptr, *unit_cnt = nullptr;
   int unit_cap = 0, unit_per_cell = 0;
   int contact_grid = 0;
+  float4 *patch_box = nullptr;  // [nslots][npatch][2] boxes of the face patches of cells that are not star-shaped (winding_patches)
+  int npatch = 0;
   // neighbour search
   NbrState *st = nullptr;
   float4 *bbox_lo = nullptr, *bbox_hi = nullptr;

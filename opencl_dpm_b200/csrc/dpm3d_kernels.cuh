@@ -66,6 +66,11 @@ struct Step3DParams {
   int *__restrict__ unit_base;
   int *__restrict__ unit_cnt;
   int unit_cap;
+  // neighbours that are NOT star-shaped about their kernel point: bounding boxes of their face patches (PATCH_F consecutive
+  // faces), refreshed every timestep by the units kernel, searched by the contact kernel (winding_patches)
+  float4 *__restrict__ patch_box;  // [cell slot][npatch][2]: (lo.xyz, 0) (hi.xyz, 0)
+  int npatch;
+  const int *__restrict__ n_total_dev;  // sharded runs: owned + ghost cells present (device-side count); else nullptr
   int nc;  // cells stepped by this launch (owned)
   int nv, nf;
   float dt, Kc;
@@ -250,12 +255,29 @@ static __device__ __noinline__ float winding_literal(const float4 *__restrict__ 
 // Omega of a SKIPPED face (den < 1e-8) in double precision from the reference's fp32 corner vectors: for a vertex
 // nearly in the plane of a face that subtends ~pi both num and den are ~1e-3, and fp32 would lose 4 digits of
 // exactly the term that W - sum(...) needs (the literal sum never evaluates these faces, so it does not suffer).
-static __device__ __noinline__ float omega_skipped_f64(float3 a, float3 b, float3 c) {
+// Only the CANCELLATIONS need the extra digits: num and den are formed in fp64 (DFMA — full rate on B200 — from the
+// reference's fp32 corner vectors); the three lengths come from one MUFU.RSQ + one Newton step in fp64 (relative error
+// ~1e-14) instead of the software fp64 sqrt, and the angle from the fp32 atan2f of the rounded pair (its ~1e-7 relative
+// error is far below the 1e-5 force tolerance; the software fp64 atan2 was most of this function's ~600 instructions).
+__device__ __forceinline__ double rsqrt_f64(double x) {
+  double r = (double)rsqrt_fast((float)x);
+  return r * (1.5 - 0.5 * x * r * r);
+}
+__device__ __forceinline__ void solid_angle_terms_f64(float3 a, float3 b, float3 c, double &den, double &num) {
   const double ax = a.x, ay = a.y, az = a.z, bx = b.x, by = b.y, bz = b.z, cx = c.x, cy = c.y, cz = c.z;
-  const double la = sqrt(ax * ax + ay * ay + az * az), lb = sqrt(bx * bx + by * by + bz * bz), lc = sqrt(cx * cx + cy * cy + cz * cz);
-  const double num = ax * (by * cz - bz * cy) + ay * (bz * cx - bx * cz) + az * (bx * cy - by * cx);
-  const double den = la * lb * lc + (ax * bx + ay * by + az * bz) * lc + (bx * cx + by * cy + bz * cz) * la + (cx * ax + cy * ay + cz * az) * lb;
-  return (float)(2.0 * atan2(num, den));
+  const double da = ax * ax + ay * ay + az * az, db = bx * bx + by * by + bz * bz, dc = cx * cx + cy * cy + cz * cz;
+  const double la = da * rsqrt_f64(da), lb = db * rsqrt_f64(db), lc = dc * rsqrt_f64(dc);
+  num = ax * (by * cz - bz * cy) + ay * (bz * cx - bx * cz) + az * (bx * cy - by * cx);
+  den = la * lb * lc + (ax * bx + ay * by + az * bz) * lc + (bx * cx + by * cy + bz * cz) * la + (cx * ax + cy * ay + cz * az) * lb;
+}
+static __device__ __noinline__ float omega_skipped_f64(float3 a, float3 b, float3 c) {
+  double den, num;
+  solid_angle_terms_f64(a, b, c, den, num);
+  // scale the pair into fp32's comfortable range (atan2 is homogeneous): both are ~|a||b||c| * 1e-3 or smaller
+  const double m = fmax(fabs(num), fabs(den));
+  if (!(m > 0.0)) return 0.0f;  // atan2(0, 0) = 0 on the reference's runtime (oracle/cl_semantics_probe.cpp)
+  const double s = 1.0 / m;
+  return 2.0f * atan2f((float)(num * s), (float)(den * s));
 }
 
 // Returns 0 on success, else the reason the caller must fall back to the literal sum (1: vertex within the pad of
@@ -365,6 +387,125 @@ __device__ __forceinline__ int winding_fast(const Step3DParams &P, bool active, 
   return why;
 }
 
+// w_ref = W - (1/4pi) * sum_{faces with den < 1e-8} Omega_f for ANY closed, consistently oriented mesh (a crumpled cell
+// that is no longer star-shaped, even a self-intersecting one: the sum of all solid angles is 4 pi W for every closed
+// oriented surface).  The neighbour's faces are grouped in patches of PATCH_F consecutive faces whose bounding boxes the
+// units kernel refreshes every timestep (only for cells that fail the star-shape test):
+//   W        signed crossings of the ray p + t * ez, t > 0: only patches whose box the ray can hit are opened; a face is
+//            crossed iff the origin lies inside its projection on z = 0 — edge functions with individually rounded
+//            products, so the two faces of an edge see exactly opposite values (watertight), ties broken by vertex index —
+//            and the triple product a.(b x c) has the sign of the projected area (crossing point above p);
+//   skipped  a skipped face has a point within rho = pad of p (CONTACT_PAD): only patches whose box comes within rho of p
+//            get the reference's den / num; for those faces the triple product is taken in fp64 so that the crossing and
+//            the sign of the skipped solid angle can never disagree about the side of the plane p is on.
+// One group of UNIT_LANES lanes per unit, group-uniform control flow.  Cost: npatch box tests + the faces of a few
+// patches, instead of all nf faces with three normalisations and an atan2 each (winding_literal).
+// Returns true if p coincides with a vertex of the neighbour (the caller takes the literal sum: normalize(0) = 0).
+constexpr int PATCH_F = 16;  // faces per patch: 2 per lane of a unit group
+static __device__ __noinline__ bool winding_patches(const ushort4 *__restrict__ faces, int nf, int npatch, const float4 *__restrict__ Vj,
+                                                    const float4 *__restrict__ box, float4 sh, float4 p, float rho, float &w_out, int g,
+                                                    int gshift, unsigned gmask) {
+  const float psx = p.x - sh.x, psy = p.y - sh.y, psz = p.z - sh.z;  // the boxes are those of the unshifted neighbour
+  const float eps = 1e-5f * (fmaxf(fabsf(psx), fmaxf(fabsf(psy), fabsf(psz))) + fmaxf(fabsf(sh.x), fmaxf(fabsf(sh.y), fabsf(sh.z))) + 1.0f);
+  const float reach = rho * 1.01f + eps;
+  int W = 0;
+  float corr = 0.0f;
+  bool coincident = false;
+  for (int base = 0; base < npatch; base += UNIT_LANES) {
+    const int k = base + g;
+    bool ray = false, near = false;
+    if (k < npatch) {
+      const float4 lo = __ldg(box + 2 * k), hi = __ldg(box + 2 * k + 1);
+      ray = psx >= lo.x - eps && psx <= hi.x + eps && psy >= lo.y - eps && psy <= hi.y + eps && psz <= hi.z + eps;
+      const float dx = fmaxf(fmaxf(lo.x - psx, psx - hi.x), 0.0f), dy = fmaxf(fmaxf(lo.y - psy, psy - hi.y), 0.0f),
+                  dz = fmaxf(fmaxf(lo.z - psz, psz - hi.z), 0.0f);
+      near = dx * dx + dy * dy + dz * dz <= reach * reach;
+    }
+    const unsigned mn = (__ballot_sync(gmask, near) >> gshift) & 0xffu;
+    unsigned m = ((__ballot_sync(gmask, ray) >> gshift) & 0xffu) | mn;
+    while (m) {  // group-uniform
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const bool nearp = (mn >> j) & 1u;
+#pragma unroll
+      for (int hf = 0; hf < PATCH_F / UNIT_LANES; hf++) {
+        const int f = (base + j) * PATCH_F + hf * UNIT_LANES + g;
+        if (f >= nf) continue;
+        const ushort4 fc = __ldg(faces + f);
+        const float4 q0 = __ldg(Vj + fc.x), q1 = __ldg(Vj + fc.y), q2 = __ldg(Vj + fc.z);
+        const float3 a = f3((q0.x + sh.x) - p.x, (q0.y + sh.y) - p.y, (q0.z + sh.z) - p.z);  // reference: V + shift - p
+        const float3 b = f3((q1.x + sh.x) - p.x, (q1.y + sh.y) - p.y, (q1.z + sh.z) - p.z);
+        const float3 c = f3((q2.x + sh.x) - p.x, (q2.y + sh.y) - p.y, (q2.z + sh.z) - p.z);
+        // edge functions of the projection, exactly antisymmetric under swapping the end points
+        const float eab = __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x));
+        const float ebc = __fsub_rn(__fmul_rn(b.x, c.y), __fmul_rn(b.y, c.x));
+        const float eca = __fsub_rn(__fmul_rn(c.x, a.y), __fmul_rn(c.y, a.x));
+        const bool pab = eab > 0.0f || (eab == 0.0f && fc.x < fc.y), pbc = ebc > 0.0f || (ebc == 0.0f && fc.y < fc.z),
+                   pca = eca > 0.0f || (eca == 0.0f && fc.z < fc.x);
+        const bool ccw = pab && pbc && pca, cw = !pab && !pbc && !pca;
+        double t = (double)(a.x * (b.y * c.z - b.z * c.y) + a.y * (b.z * c.x - b.x * c.z) + a.z * (b.x * c.y - b.y * c.x));
+        if (nearp) {
+          float den, num;
+          solid_angle_terms(a, b, c, den, num);
+          if (den < 1e-8f) {  // skipped by the reference (:293-295)
+            double den64, num64;
+            solid_angle_terms_f64(a, b, c, den64, num64);
+            t = num64;
+            const double mm = fmax(fabs(num64), fabs(den64));
+            if (mm > 0.0) corr += 2.0f * atan2f((float)(num64 / mm), (float)(den64 / mm));
+          }
+          coincident = coincident || dot3(a, a) == 0.0f || dot3(b, b) == 0.0f || dot3(c, c) == 0.0f;
+        }
+        // crossing point above p  <=>  the triple product has the sign of the projected area
+        if (ccw && t > 0.0) W += 1;   // the ray leaves through a face whose normal points up
+        if (cw && t < 0.0) W -= 1;    // the ray enters
+      }
+    }
+  }
+#pragma unroll
+  for (int o = UNIT_LANES / 2; o > 0; o >>= 1) {
+    W += __shfl_xor_sync(gmask, W, o);
+    corr += __shfl_xor_sync(gmask, corr, o);
+  }
+  w_out = (float)W - corr / (4.0f * 3.14159274101257f);
+  return ((__ballot_sync(gmask, coincident) >> gshift) & 0xffu) != 0u;
+}
+
+// Bounding boxes of the face patches of one cell (not star-shaped): 8 lanes per patch, 2 faces each; exact fp32 min / max.
+__device__ __forceinline__ void patch_boxes(const Step3DParams &P, int ci, int tid, int nthreads) {
+  const float4 *V = P.pos_in + (size_t)ci * P.nv;
+  float4 *box = P.patch_box + (size_t)ci * P.npatch * 2;
+  const int g = tid & (UNIT_LANES - 1);
+  const int per = nthreads / UNIT_LANES;
+  for (int k0 = 0; k0 < P.npatch; k0 += per) {  // uniform trip count over the CTA (full-warp shuffles below)
+    const int k = k0 + tid / UNIT_LANES;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (k < P.npatch) {
+#pragma unroll
+      for (int hf = 0; hf < PATCH_F / UNIT_LANES; hf++) {
+        const int f = k * PATCH_F + hf * UNIT_LANES + g;
+        if (f >= P.nf) continue;
+        const ushort4 fc = __ldg(P.faces + f);
+        const float4 q0 = V[fc.x], q1 = V[fc.y], q2 = V[fc.z];
+        lo[0] = fminf(lo[0], fminf(q0.x, fminf(q1.x, q2.x))); hi[0] = fmaxf(hi[0], fmaxf(q0.x, fmaxf(q1.x, q2.x)));
+        lo[1] = fminf(lo[1], fminf(q0.y, fminf(q1.y, q2.y))); hi[1] = fmaxf(hi[1], fmaxf(q0.y, fmaxf(q1.y, q2.y)));
+        lo[2] = fminf(lo[2], fminf(q0.z, fminf(q1.z, q2.z))); hi[2] = fmaxf(hi[2], fmaxf(q0.z, fmaxf(q1.z, q2.z)));
+      }
+    }
+#pragma unroll
+    for (int o = UNIT_LANES / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+        hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+      }
+    if (k < P.npatch && g == 0) {
+      box[2 * k] = make_float4(lo[0], lo[1], lo[2], 0.f);
+      box[2 * k + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // K1a: contact units.  One CTA per cell: every vertex is tested against the padded bounding box and sphere of each
 // candidate neighbour (cell list) whose box overlaps the cell's own; survivors are written, ordered by (thread,
@@ -385,6 +526,11 @@ __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams
   const int ci = blockIdx.x, nv = P.nv, K = P.K;
   griddep_launch();
   // state of the previous timestep's step kernel (complete before the kernel ahead of this one started): read it now
+  if (ci >= (P.n_total_dev ? *P.n_total_dev : P.nc)) return;  // sharded: the grid covers the ghost capacity
+  // a cell that is not star-shaped about its kernel point (owned or ghost): refresh the boxes of its face patches, which the
+  // contact kernel searches for every unit that has this cell as the neighbour (winding_patches)
+  if (P.bnd_in[BND * (size_t)ci + 3].y == 0.0f) patch_boxes(P, ci, tid, UNITS_THREADS);
+  if (ci >= P.nc) return;  // ghost cell: no units of its own
   const float4 bi0 = P.bnd_in[BND * (size_t)ci], bi1 = P.bnd_in[BND * (size_t)ci + 1], bi2 = P.bnd_in[BND * (size_t)ci + 2];
   constexpr bool att = ATT;
   const float l0i = att ? P.bnd_in[BND * (size_t)ci + 3].w : 0.0f;
@@ -584,10 +730,14 @@ __global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(Step3DPa
     }
     float w = 0.0f;
     int why = winding_fast(P, contact && star, Vj, sh, p, f3(bj2.x + sh.x, bj2.y + sh.y, bj2.z + sh.z), bj1.w, w, g, gshift);
-    if (contact && !star) why = -1;
+    if (contact && !star) {  // group-uniform branch: the general evaluation over the neighbour's patch boxes
+      const bool coincident = winding_patches(P.faces, P.nf, P.npatch, Vj, P.patch_box + (size_t)cj * P.npatch * 2, sh, p, bj1.w, w, g, gshift, gmask);
+      why = coincident ? 1 : 0;
+      if (g == 0) atomicAdd(&P.st->fallback_why[0], 1ull);  // statistics: units of non-star-shaped neighbours
+    }
     if (contact && why != 0) {  // group-uniform branch
       w = winding_literal(Vj, P.faces, P.nf, sh, p, g, gmask);
-      if (g == 0) { atomicAdd(&P.st->literal_evals, 1ull); atomicAdd(&P.st->fallback_why[why < 0 ? 0 : why], 1ull); }
+      if (g == 0) { atomicAdd(&P.st->literal_evals, 1ull); atomicAdd(&P.st->fallback_why[why], 1ull); }
     }
     if (active && g == 0) P.unit_w[u] = contact ? w : 0.0f;
     if (att) {

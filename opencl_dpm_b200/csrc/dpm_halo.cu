@@ -332,12 +332,13 @@ int dpm3d_shard_init(dpm3d_t *h, int rank, int nranks, const uint8_t id[128], in
   // regrow every per-cell array that also holds ghosts
   const size_t nvert = (size_t)h->nslots * h->nv;
   void **grow[] = {(void **)&h->pos[0], (void **)&h->pos[1], (void **)&h->bnd[0], (void **)&h->bnd[1], (void **)&h->bbox_lo,
-                   (void **)&h->bbox_hi, (void **)&h->bin_id, (void **)&h->order, (void **)&h->bin_count, (void **)&h->bin_start};
+                   (void **)&h->bbox_hi, (void **)&h->bin_id, (void **)&h->order, (void **)&h->bin_count, (void **)&h->bin_start,
+                   (void **)&h->patch_box};
   h->cap = 4 * h->nslots + 1024;
   const size_t sizes[] = {sizeof(float4) * nvert, sizeof(float4) * nvert, sizeof(float4) * BND * h->nslots, sizeof(float4) * BND * h->nslots,
                           sizeof(float4) * h->nslots, sizeof(float4) * h->nslots, sizeof(int) * h->nslots, sizeof(int) * h->nslots,
-                          sizeof(int) * (h->cap + 1), sizeof(int) * (h->cap + 1)};
-  for (int i = 0; i < 10; i++) {
+                          sizeof(int) * (h->cap + 1), sizeof(int) * (h->cap + 1), sizeof(float4) * 2 * (size_t)h->npatch * h->nslots};
+  for (int i = 0; i < 11; i++) {
     if (*grow[i]) cudaFree(*grow[i]);
     *grow[i] = nullptr;
     DPM_CUDA_TRY(cudaMalloc(grow[i], sizes[i]));

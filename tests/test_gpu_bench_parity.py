@@ -7,7 +7,7 @@ and shaders/Cell2D_kernel.cl:121-268; the culled form equals the all-pairs form 
 on the same positions.  Tolerance: helpers.assert_forces_close — every vertex within 1e-5 * max(|F_ref|_inf, 1e-3) of the
 fp32 oracle, the few ill-conditioned vertices within 8x the oracle's own fp32-vs-fp64 error.
 Also: timestep 5 from the raw lattice (contact-dominated: ~10^5 units), and a deliberately NON-star-shaped tissue whose
-contacts all take the literal fallback of the contact kernel."""
+contacts all take the general (patch-box) evaluation of the contact kernel instead of the star-shaped fast path."""
 import numpy as np
 import pytest
 
@@ -36,7 +36,7 @@ def _culled3d(O, d, V, dtype=np.float32, which=15, want_contacts=False):
                       dtype=dtype, want_contacts=want_contacts)
 
 
-def _check_one_more_step_3d(d, V0, presteps, what, min_units=0, min_literal=0):
+def _check_one_more_step_3d(d, V0, presteps, what, min_units=0, min_nonstar=0, min_contacts=0):
     """GPU: upload V0, advance `presteps` timesteps, download -> V; upload V, ONE timestep -> (V1, F).  Oracle on V."""
     from opencl_dpm_b200 import Dpm3D
 
@@ -53,7 +53,9 @@ def _check_one_more_step_3d(d, V0, presteps, what, min_units=0, min_literal=0):
     h.step(1, *args)
     V1, F = h.download()
     st = h.stats()
-    units, literal = int(st.contact_evals), int(st.reserved[0])
+    # reserved[0]: units that fell back to the literal all-faces sum; reserved[1] low word: units whose neighbour is not
+    # star-shaped (general patch-box evaluation)
+    units, literal, nonstar = int(st.contact_evals), int(st.reserved[0]), int(st.reserved[1] & 0xffffffff)
     Fref, con = _culled3d(O, d, V, want_contacts=True)
     F64 = _culled3d(O, d, V, dtype=np.float64)
     worst, nbad = H.assert_forces_close(F[:, :3], Fref[:, :3], F64[:, :3], what)
@@ -76,10 +78,11 @@ def _check_one_more_step_3d(d, V0, presteps, what, min_units=0, min_literal=0):
     assert ndiff <= max(2, int(2e-4 * ref_has.sum())), f"{what}: contact sets differ at {ndiff} vertices of {int(ref_has.sum())} in contact"
     h.close()
     print(f"{what}: |F|max {np.abs(Fref).max():.3f}, worst err/tol {worst:.2f}, ill-conditioned beyond tol {nbad}, units/step {units}, "
-          f"literal fallbacks {literal}, vertices in contact {int(ref_has.sum())} (set differs at {ndiff})")
+          f"non-star units {nonstar}, literal fallbacks {literal}, vertices in contact {int(ref_has.sum())} (set differs at {ndiff})")
     assert units >= min_units, f"{what}: only {units} contact units — not the regime this test is for"
-    assert literal >= min_literal, f"{what}: only {literal} literal-fallback units"
-    return units, literal
+    assert nonstar >= min_nonstar, f"{what}: only {nonstar} units with a non-star-shaped neighbour"
+    assert int(ref_has.sum()) >= min_contacts, f"{what}: only {int(ref_has.sum())} vertices carry a contact force"
+    return units, nonstar, literal
 
 
 @pytest.mark.parametrize("subdiv,name", [(3, "D642"), (2, "D162")])
@@ -91,13 +94,27 @@ def test_bench_batch_3d_one_more_step(subdiv, name):
     _check_one_more_step_3d(d, d["verts"], 100, f"{name} batch (lattice + 100 timesteps)")
 
 
-def test_contact_dominated_timestep_from_the_raw_lattice():
-    """Timestep 5 of config D from the raw lattice: every cell overlaps its neighbours, ~10^5 contact units per timestep —
-    the regime the headline batch has left behind (`trajectory` phase 0-30 of the bench line)."""
+@pytest.mark.parametrize("presteps", [0, 1, 5])
+def test_contact_dominated_timesteps_from_the_raw_lattice(presteps):
+    """The first timesteps of config D from the raw lattice: every cell overlaps its neighbours, ~10^5-10^6 contact units
+    per timestep, thousands of vertices inside a neighbour at timestep 0 — the regime the headline batch has left behind
+    (`trajectory` phase 0-30 of the bench line)."""
     from opencl_dpm_b200 import synth
 
     d = synth.monolayer3d(64, subdiv=3)
-    _check_one_more_step_3d(d, d["verts"], 5, "D642 timestep 5 from the lattice", min_units=20000)
+    _check_one_more_step_3d(d, d["verts"], presteps, f"D642 timestep {presteps} from the lattice", min_units=20000,
+                            min_contacts=1000 if presteps == 0 else 0)
+
+
+@pytest.mark.parametrize("subdiv,name", [(2, "C162"), (3, "C642")])
+def test_bench_batch_config_c(subdiv, name):
+    """BASELINE config C as bench.py runs it (reference test3D.py: 64 cells placed by Disperse2D() with their centres ON the
+    substrate plane, + 100 timesteps): the substrate force folds the lower half of every cell inwards, no cell is star-shaped
+    any more, every contact unit takes the general patch-box evaluation."""
+    from opencl_dpm_b200 import synth
+
+    d = synth.test3d_config(64, subdiv=subdiv)
+    _check_one_more_step_3d(d, d["verts"], 100, f"{name} batch (Disperse2D + 100 timesteps)", min_units=1000, min_nonstar=1000)
 
 
 def _dimpled(d, depth=1.4, cap=0.5):
@@ -110,17 +127,18 @@ def _dimpled(d, depth=1.4, cap=0.5):
     return V.reshape(-1, 4)
 
 
-def test_non_star_shaped_tissue_takes_the_literal_fallback_in_bulk():
+def test_non_star_shaped_tissue_takes_the_general_evaluation():
     """256 dimpled cells (162 vertices) on the overlapping lattice: every neighbour fails the star-shape test, so every
-    contact unit (>= 10^3) is evaluated by the literal all-faces sum — the path a crumpled tissue lives on."""
+    contact unit (>= 10^3) is evaluated by the general patch-box evaluation — the path a crumpled tissue lives on."""
     from opencl_dpm_b200 import synth
 
     d = synth.monolayer3d(16, subdiv=2)
     V0 = _dimpled(d)
-    units, literal = _check_one_more_step_3d(d, V0, 0, "non-star tissue", min_units=1000, min_literal=1000)
-    assert literal == units, "every unit of a non-star-shaped neighbour must take the literal sum"
+    units, nonstar, literal = _check_one_more_step_3d(d, V0, 0, "non-star tissue", min_units=1000, min_nonstar=1000, min_contacts=1000)
+    assert nonstar == units, "every neighbour is non-star-shaped: every unit takes the general evaluation"
+    assert literal <= units // 100, "the literal all-faces sum is only the fallback for coincident vertices"
     # and a few timesteps later (the dimples relax but stay): still in parity
-    _check_one_more_step_3d(d, V0, 8, "non-star tissue + 8 timesteps", min_units=1000, min_literal=500)
+    _check_one_more_step_3d(d, V0, 8, "non-star tissue + 8 timesteps", min_units=1000, min_nonstar=500)
 
 
 def test_bench_batch_2d_one_more_step():
