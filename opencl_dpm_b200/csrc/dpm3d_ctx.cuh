@@ -36,6 +36,11 @@ struct dpm3d_ctx {
   int *unit_base = nullptr, *unit_cnt = nullptr;
   int unit_cap = 0, unit_per_cell = 0;
   int contact_grid = 0;
+  uint16_t *vorder = nullptr;   // [nv] vertex taken by processing slot r of the step kernel's ring pass (bank-conflict-aware order)
+  ushort4 *faces_proc = nullptr;  // [nf] (a, b, c, face id) in the processing order of the step kernel's face pass
+  float *terms = nullptr;     // [nc][terms_stride(nf)] signed-volume terms of the new positions (step kernel face pass -> group chain warp)
+  float4 *part = nullptr;     // [nc][4 warps][3] per-warp partials of the step kernel's epilogue (folded by the group's chain warp)
+  int *grp_done = nullptr;    // [ceil(nc / CHAIN_GROUP)] group completion counters of the step kernel (self-resetting)
   float4 *patch_box = nullptr;  // [nslots][npatch][2] boxes of the face patches of cells that are not star-shaped (winding_patches)
   int npatch = 0;
   // neighbour search

@@ -40,12 +40,12 @@ struct Step3DParams {
   const float4 *__restrict__ cellA;  // (Kv, Ka, Ks, v0)
   const float4 *__restrict__ cellB;  // (a0, l0, 0, 0)
   const ushort4 *__restrict__ faces;
-  const uint16_t *__restrict__ ring_nbr;   // [nv][ring_stride], ring_stride == 8 (one 16-byte load per vertex) or 16
+  const uint16_t *__restrict__ ring_nbr;   // [nv][ring_stride] BYTE OFFSETS (16 * vertex) of the ring neighbours; ring_stride == 8 (one 16-byte load) or 16
   const uint16_t *__restrict__ ring_face;
   const uint8_t *__restrict__ valence;
   int ring_stride;
-  const unsigned char *__restrict__ flag_in;  // [cell][nf] per-face flags of the CURRENT positions (bit0 facing the substrate,
-  unsigned char *__restrict__ flag_out;       //   bit1 degenerate edge), written by the previous epilogue / bounds kernel
+  const unsigned char *__restrict__ flag_in;  // [cell][vflag_stride(nv)] per-vertex flags of the CURRENT positions (see vflag_stride),
+  unsigned char *__restrict__ flag_out;       //   written by the previous epilogue / the bounds kernel
   uint2 *__restrict__ vlist;                  // [cell][<= nv] the cell's vertices that have units: (vertex, (offset within the
   int *__restrict__ vlist_cnt;                //   cell's unit range) << 8 | count), and how many there are
   const ushort4 *__restrict__ face_adj;    // face across edge (a,b), (b,c), (c,a)
@@ -68,6 +68,11 @@ struct Step3DParams {
   int unit_cap;
   // neighbours that are NOT star-shaped about their kernel point: bounding boxes of their face patches (PATCH_F consecutive
   // faces), refreshed every timestep by the units kernel, searched by the contact kernel (winding_patches)
+  const uint16_t *__restrict__ vorder;     // [nv] vertex taken by slot r of the ring pass (chosen on the host against bank conflicts)
+  const ushort4 *__restrict__ faces_proc;  // [nf] (a, b, c, face id) in the face pass's processing order (a permutation inside blocks of 32)
+  float *__restrict__ terms;       // [owned cell][terms_stride(nf)] signed-volume terms of the NEW positions (face pass -> chain warp)
+  int *__restrict__ grp_done;      // [ceil(nc / CHAIN_GROUP)] CTAs of the group that have published their cell (self-resetting)
+  float4 *__restrict__ part;       // [owned cell][STEP_WARPS][3] per-warp partials of the new positions: (lo.xyz, r2) (hi.xyz, 0) (e2, star, 0, 0)
   float4 *__restrict__ patch_box;  // [cell slot][npatch][2]: (lo.xyz, 0) (hi.xyz, 0)
   int npatch;
   const int *__restrict__ n_total_dev;  // sharded runs: owned + ghost cells present (device-side count); else nullptr
@@ -90,10 +95,23 @@ struct Step3DParams {
 #define DPM_RING_UNROLL 1
 #endif
 #ifndef DPM_STEP_MINB
-#define DPM_STEP_MINB 1  // CTAs per SM promised to ptxas for the step kernel (1 = no register cap); see profiles/ for the sweep
+#define DPM_STEP_MINB 9  // CTAs per SM promised to ptxas for the step kernel: 56 registers, no spills in the default instantiation
 #endif
-constexpr int BND = 4;              // float4 per cell in the bounds arrays:
-                                    //   (lo.xyz, r2max) (hi.xyz, contact pad) (com.xyz, volume) (r2min, star flag, 0, 0)
+constexpr int BND = 5;              // float4 per cell in the bounds arrays:
+                                    //   (lo.xyz, r2max about the kernel point) (hi.xyz, contact pad) (com.xyz, volume)
+                                    //   (0, star flag, previous volume, l0) (kernel point.xyz, 0)
+// The KERNEL POINT of a cell is an interior point fixed BEFORE the cell's new positions exist (the serial-order COM of the
+// positions one timestep earlier; after an upload the COM itself): the centre of the bounding sphere, the apex of the
+// star-shape test and the point the contact kernel walks from.  Nothing of the step kernel's epilogue therefore waits for
+// the serial COM / volume chains of the NEW positions; those only feed the next timestep (shift, force direction, strain).
+constexpr int CHAIN_GROUP = 8;      // cells whose serial chains one warp evaluates together (4 chains per cell = 32 lanes)
+constexpr int CHAIN_CH = 32;        // chain iterations staged per chunk
+constexpr int CHAIN_STAGES = 3;     // chunks in flight (cp.async groups)
+constexpr int CHAIN_POS_STRIDE = CHAIN_CH * 16 + 16;  // bytes per cell and stage, padded: the 8 cells' lanes hit 8 different bank quads
+constexpr int CHAIN_TERM_STRIDE = CHAIN_CH * 8 + 16;
+constexpr int CHAIN_STAGE_BYTES = CHAIN_GROUP * (CHAIN_POS_STRIDE + CHAIN_TERM_STRIDE);
+constexpr int CHAIN_SMEM = CHAIN_STAGES * CHAIN_STAGE_BYTES;
+__host__ __device__ inline int terms_stride(int nf) { return ((nf + 2 * CHAIN_CH - 1) / (2 * CHAIN_CH)) * (2 * CHAIN_CH); }  // floats per cell
 // The reference skips faces with denom < 1e-8 (shaders/Cell3D_Kernel.cl:293-295), i.e. every face that subtends
 // at least pi steradians from the vertex, so its "winding number" is
 //        w_ref(p) = W(p) - (1/4pi) * sum over skipped faces of Omega_f(p),      W = true winding number (0 or 1).
@@ -119,11 +137,21 @@ __device__ __forceinline__ float group_sum(float v, unsigned gmask) {
   return v;
 }
 
-// sP[nv] | sF[max(nv, ceil(nf/2))] (forces; the epilogue reuses it for the signed-volume terms, two per float4 so that the
-// serial chains read them with the vertex stride) | sFlag[nf]
+// sP[nv] | sF[max(nv, ceil(nf/2))] (forces; the bounds kernel reuses it for the signed-volume terms) | per-vertex flags in | out
 __host__ __device__ inline int step3d_mid_slots(int nv, int nf) { return nv > (nf + 1) / 2 ? nv : (nf + 1) / 2; }
+// per-VERTEX flags of a cell (one byte per vertex, rows padded to 16 bytes for the bulk copies): bits 0..6 = number of
+// adjacent faces that face the substrate (StickToSurface applies once per such face, :226-246), bit 7 = some adjacent face
+// has a degenerate edge (SurfaceAreaForceUpdate skips it, :151).  Accumulated by the face pass of the previous epilogue.
+__host__ __device__ inline int vflag_stride(int nv) { return (nv + 15) & ~15; }
+__device__ __forceinline__ void vflag_add(unsigned char *sV, int v, unsigned bits) {
+  atomicAdd(reinterpret_cast<unsigned *>(sV) + (v >> 2), bits << (8 * (v & 3)));
+}
+__device__ __forceinline__ void vflag_or(unsigned char *sV, int v, unsigned bits) {
+  atomicOr(reinterpret_cast<unsigned *>(sV) + (v >> 2), bits << (8 * (v & 3)));
+}
 inline size_t step3d_smem_bytes(int nv, int nf) {
-  return sizeof(float4) * ((size_t)nv + step3d_mid_slots(nv, nf)) + ((nf + 15) / 16) * 16 + 64;
+  const size_t cell = sizeof(float4) * ((size_t)nv + step3d_mid_slots(nv, nf)) + 2 * (size_t)vflag_stride(nv) + 64;
+  return cell > (size_t)CHAIN_SMEM ? cell : (size_t)CHAIN_SMEM;  // the chain warp of a group's last CTA stages 8 cells in the same memory
 }
 
 __device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
@@ -529,17 +557,12 @@ __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams
   if (ci >= (P.n_total_dev ? *P.n_total_dev : P.nc)) return;  // sharded: the grid covers the ghost capacity
   // a cell that is not star-shaped about its kernel point (owned or ghost): refresh the boxes of its face patches, which the
   // contact kernel searches for every unit that has this cell as the neighbour (winding_patches)
-  if (P.bnd_in[BND * (size_t)ci + 3].y == 0.0f) patch_boxes(P, ci, tid, UNITS_THREADS);
+  const float4 bi0 = P.bnd_in[BND * (size_t)ci], bi1 = P.bnd_in[BND * (size_t)ci + 1], bi2 = P.bnd_in[BND * (size_t)ci + 2],
+               bi3 = P.bnd_in[BND * (size_t)ci + 3];
+  if (bi3.y == 0.0f) patch_boxes(P, ci, tid, UNITS_THREADS);
   if (ci >= P.nc) return;  // ghost cell: no units of its own
-  const float4 bi0 = P.bnd_in[BND * (size_t)ci], bi1 = P.bnd_in[BND * (size_t)ci + 1], bi2 = P.bnd_in[BND * (size_t)ci + 2];
   constexpr bool att = ATT;
-  const float l0i = att ? P.bnd_in[BND * (size_t)ci + 3].w : 0.0f;
-  float4 myp[UNITS_VPT];
-#pragma unroll
-  for (int j = 0; j < UNITS_VPT; j++) {
-    const int v = tid + j * UNITS_THREADS;
-    myp[j] = (v < nv) ? P.pos_in[(size_t)ci * nv + v] : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  const float l0i = att ? bi3.w : 0.0f;
   griddep_wait();  // the candidate lists (and the unit counter) belong to the rebuild kernel ahead
   const int ncand = min(P.cand_count[ci], K);
   int nact = 0;
@@ -570,7 +593,8 @@ __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams
     float4 lo = make_float4((bj0.x + sh.x) - pad, (bj0.y + sh.y) - pad, (bj0.z + sh.z) - pad, 0.f);
     float4 hi = make_float4((bj1.x + sh.x) + pad, (bj1.y + sh.y) + pad, (bj1.z + sh.z) + pad, 0.f);
     const float rs = sqrtf(bj0.w) + pad;
-    float4 sph = make_float4(bj2.x + sh.x, bj2.y + sh.y, bj2.z + sh.z, rs * rs * 1.0001f + 1e-30f);
+    const float4 bj4 = P.bnd_in[BND * (size_t)cj + 4];  // kernel point: centre of cj's bounding sphere
+    float4 sph = make_float4(bj4.x + sh.x, bj4.y + sh.y, bj4.z + sh.z, rs * rs * 1.0001f + 1e-30f);
     if (nocull) {
       lo = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
       hi = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
@@ -583,9 +607,15 @@ __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams
     sSph[k] = sph;
     nact += ov ? 1 : 0;
   }
-  if (__syncthreads_or(nact) == 0) {  // no neighbour's box reaches this cell
+  if (__syncthreads_or(nact) == 0) {  // no neighbour's box reaches this cell: its vertices are not even read
     if (tid == 0) { P.unit_base[ci] = 0; P.unit_cnt[ci] = 0; P.vlist_cnt[ci] = 0; }
     return;
+  }
+  float4 myp[UNITS_VPT];
+#pragma unroll
+  for (int j = 0; j < UNITS_VPT; j++) {
+    const int v = tid + j * UNITS_THREADS;
+    myp[j] = (v < nv) ? P.pos_in[(size_t)ci * nv + v] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   // One pass of tests: with at most 32 candidates (the default capacity) the survivors of a vertex are kept as a bit mask
   // and the emit pass below only walks the set bits; longer lists repeat the tests when emitting.
@@ -704,6 +734,7 @@ __global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(Step3DPa
     const float4 p = P.pos_in[rec.x];
     const float4 bi2 = P.bnd_in[BND * (size_t)ci + 2];
     const float4 bj1 = P.bnd_in[BND * (size_t)cj + 1], bj2 = P.bnd_in[BND * (size_t)cj + 2], bj3 = P.bnd_in[BND * (size_t)cj + 3];
+    const float4 bj4 = P.bnd_in[BND * (size_t)cj + 4];  // kernel point of cj: sphere centre, apex of its star-shape test
     constexpr bool att = ATT;
     float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
     if (P.pbc) {  // shift = L * round((COMi - COMJ) / L)   (:277-281)
@@ -712,7 +743,7 @@ __global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(Step3DPa
       sh.z = P.L * roundf((bi2.z - bj2.z) / P.L);
     }
     const float4 *Vj = P.pos_in + (size_t)cj * nv;
-    const bool star = bj3.y != 0.0f;  // neighbour star-shaped about its COM (checked by its owner's epilogue)
+    const bool star = bj3.y != 0.0f;  // neighbour star-shaped about its kernel point (checked by its owner's epilogue)
     // With the attraction on, the units kernel admits vertices within the (larger) attraction pad: the contact term is
     // evaluated only for those that pass the units kernel's test with the CONTACT pad (same expressions), the others get
     // w = 0 exactly as if they had been culled.
@@ -724,12 +755,12 @@ __global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(Step3DPa
       const float lx = (bj0.x + sh.x) - pad, ly = (bj0.y + sh.y) - pad, lz = (bj0.z + sh.z) - pad;
       const float hx = (bj1.x + sh.x) + pad, hy = (bj1.y + sh.y) + pad, hz = (bj1.z + sh.z) + pad;
       const float rs = sqrtf(bj0.w) + pad;
-      const float dx = p.x - (bj2.x + sh.x), dy = p.y - (bj2.y + sh.y), dz = p.z - (bj2.z + sh.z);
+      const float dx = p.x - (bj4.x + sh.x), dy = p.y - (bj4.y + sh.y), dz = p.z - (bj4.z + sh.z);
       contact = contact && !(p.x < lx || p.x > hx || p.y < ly || p.y > hy || p.z < lz || p.z > hz) &&
                 (dx * dx + dy * dy + dz * dz) <= rs * rs * 1.0001f + 1e-30f;
     }
     float w = 0.0f;
-    int why = winding_fast(P, contact && star, Vj, sh, p, f3(bj2.x + sh.x, bj2.y + sh.y, bj2.z + sh.z), bj1.w, w, g, gshift);
+    int why = winding_fast(P, contact && star, Vj, sh, p, f3(bj4.x + sh.x, bj4.y + sh.y, bj4.z + sh.z), bj1.w, w, g, gshift);
     if (contact && !star) {  // group-uniform branch: the general evaluation over the neighbour's patch boxes
       const bool coincident = winding_patches(P.faces, P.nf, P.npatch, Vj, P.patch_box + (size_t)cj * P.npatch * 2, sh, p, bj1.w, w, g, gshift, gmask);
       why = coincident ? 1 : 0;
@@ -796,7 +827,10 @@ __device__ __forceinline__ bool face_sees_centre(float4 P0, float3 n, float nn, 
 // sum and partial AABB of the vertices it staged / integrated (tid, tid + STEP_THREADS, ...).
 //   bnd[0] = (lo.xyz, r2max)   bnd[1] = (hi.xyz, pad)   bnd[2] = (com.xyz, volume)   bnd[3] = (r2min, star, vol_prev, l0)
 // ---------------------------------------------------------------------------------
-constexpr int STEP_THREADS = 128;
+#ifndef DPM_STEP_THREADS
+#define DPM_STEP_THREADS 128
+#endif
+constexpr int STEP_THREADS = DPM_STEP_THREADS;
 constexpr int STEP_WARPS = STEP_THREADS / 32;
 
 struct CellTopo {
@@ -821,9 +855,9 @@ struct VertPartial {  // per-thread partials over the thread's own vertices
   }
 };
 
-__device__ __forceinline__ void cell_scalars(const float4 *sP, float4 *sWide, const CellTopo &T, VertPartial vp, float vol_prev, const float *l0_ptr,
-                                             float4 *bnd_cell, unsigned char *flag_cell, const float4 *bbox_lo, const float4 *bbox_hi,
-                                             NbrState *st) {
+__device__ __forceinline__ void cell_scalars(const float4 *sP, float4 *sWide, unsigned char *sV, const CellTopo &T, VertPartial vp, float vol_prev,
+                                             const float *l0_ptr, float4 *bnd_cell, unsigned char *flag_cell, const float4 *bbox_lo,
+                                             const float4 *bbox_hi, NbrState *st) {
   __shared__ float sRed[STEP_WARPS][12];
   __shared__ float sSc[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -870,11 +904,18 @@ __device__ __forceinline__ void cell_scalars(const float4 *sP, float4 *sWide, co
     const float la = dot3(A, A), lb = dot3(B, B), lc = dot3(C, C);
     e2 = fmaxf(e2, fmaxf(la, fmaxf(lb, lc)));  // every edge is an edge of some face: longest edge for free
     const bool deg = fminf(la, fminf(lb, lc)) < 1e-24f;
-    flag_cell[f] = (unsigned char)((down ? 1 : 0) | (deg ? 2 : 0));
+    if (down) {  // only corners the substrate force can act on (below the plane or within 2 l0 of it)
+      const float near_z = *l0_ptr * 2.0f;
+      if (P0.z < near_z) vflag_add(sV, fc.x, 1u);
+      if (P1.z < near_z) vflag_add(sV, fc.y, 1u);
+      if (P2.z < near_z) vflag_add(sV, fc.z, 1u);
+    }
+    if (deg) { vflag_or(sV, fc.x, 0x80u); vflag_or(sV, fc.y, 0x80u); vflag_or(sV, fc.z, 0x80u); }
   }
   e2 = warp_max(e2);
   if (lane == 0) sRed[warp][9] = e2;
   __syncthreads();
+  for (int v = tid; v < vflag_stride(nv); v += STEP_THREADS) flag_cell[v] = sV[v];
   // The serial chains (:35-44 COM, :46-64 volume): lane 0/1/2 = COM x/y/z, lane 3 = signed volume.  Every iteration
   // is one 8-byte LDS with the same 16-byte stride in all four lanes (lanes 0,1: sP[k].xy; lane 2: sP[k].zw; lane 3:
   // sWide[k].xy = terms 2k, 2k+1) and two predicated FADDs.
@@ -923,6 +964,7 @@ __device__ __forceinline__ void cell_scalars(const float4 *sP, float4 *sWide, co
     bnd_cell[1] = make_float4(h[0], h[1], h[2], pad);
     bnd_cell[2] = make_float4(com.x, com.y, com.z, sSc[3]);
     bnd_cell[3] = make_float4(rm, star ? 1.f : 0.f, vol_prev, *l0_ptr);  // l0 travels with the bounds (ghost cells have no parameters)
+    bnd_cell[4] = make_float4(com.x, com.y, com.z, 0.f);                 // kernel point of freshly uploaded positions: their own COM
     if (st) {  // neighbour-list validity
       const float4 bl = *bbox_lo, bh = *bbox_hi;
       if (l[0] < bl.x || l[1] < bl.y || l[2] < bl.z || h[0] > bh.x || h[1] > bh.y || h[2] > bh.z) st->rebuild = 1;
@@ -935,8 +977,10 @@ static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_bounds_kernel(const
                                                                            CellTopo T, const float4 *cellB) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 *sP = reinterpret_cast<float4 *>(smem_raw);
-  float4 *sWide = sP + T.nv;  // same carve-up as the step kernel (sP | sF | sFlag)
+  float4 *sWide = sP + T.nv;  // same carve-up as the step kernel (sP | sF | vertex flags)
+  unsigned char *sV = reinterpret_cast<unsigned char *>(sWide + step3d_mid_slots(T.nv, T.nf));
   const int ci = blockIdx.x;
+  for (int v = threadIdx.x; v < vflag_stride(T.nv) / 4; v += STEP_THREADS) reinterpret_cast<unsigned *>(sV)[v] = 0u;
   VertPartial vp;
   vp.init();
   for (int v = threadIdx.x; v < T.nv; v += STEP_THREADS) {
@@ -945,7 +989,7 @@ static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_bounds_kernel(const
     vp.add(p);
   }
   __syncthreads();
-  cell_scalars(sP, sWide, T, vp, 0.0f, &cellB[ci].y, bnd + BND * (size_t)ci, flags + (size_t)ci * T.nf, nullptr, nullptr, nullptr);
+  cell_scalars(sP, sWide, sV, T, vp, 0.0f, &cellB[ci].y, bnd + BND * (size_t)ci, flags + (size_t)ci * vflag_stride(T.nv), nullptr, nullptr, nullptr);
 }
 
 // Walk-start table of the fast contact evaluation: for the direction of each octahedral texel, the face of cell 0 whose
@@ -1011,8 +1055,36 @@ static __global__ void __launch_bounds__(STEP_THREADS) dpm3d_dirtable_kernel(con
 // :66-112).  DEG: some ring face of this warp's vertices has a degenerate edge (rare) -> per-edge weights; otherwise
 // every edge counts twice.  COMPAT: reference-race mode, the gradient is split by face index and taken about the COM
 // like the reference; otherwise it is taken about the vertex itself (same sum over a closed ring, smaller terms).
+__device__ __forceinline__ float4 lds_off(const float4 *sP, unsigned off) {
+  return *reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(sP) + off);
+}
+// Degenerate ring faces of one vertex, from the geometry (rare path: some face at this warp's vertices has an edge shorter
+// than 1e-12, SurfaceAreaForceUpdate :151): bit i <=> ring face i = (v, n_i, n_{i+1}) has such an edge.  The three squared
+// lengths are the same fp32 values the face pass compared, so both sides agree on which faces are skipped.
+template <int MAXV, int MINV>
+__device__ __forceinline__ unsigned ring_deg_mask(const float4 *sP, const unsigned short (&ro)[MAXV], int val, float4 Pv) {
+  unsigned m = 0u;
+  float3 E0 = f3(0.f, 0.f, 0.f), Ep = E0;
+  float l0 = 0.f, lp = 0.f;
+  int last = 0;
+#pragma unroll
+  for (int i = 0; i < MAXV; i++) {
+    if (i >= MINV && i >= val) break;
+    const float3 E = sub3(lds_off(sP, ro[i]), Pv);
+    const float l2 = dot3(E, E);
+    if (i == 0) { E0 = E; l0 = l2; }
+    else {
+      const float3 D = f3(E.x - Ep.x, E.y - Ep.y, E.z - Ep.z);
+      if (fminf(lp, fminf(l2, dot3(D, D))) < 1e-24f) m |= 1u << (i - 1);
+    }
+    Ep = E; lp = l2; last = i;
+  }
+  const float3 D = f3(E0.x - Ep.x, E0.y - Ep.y, E0.z - Ep.z);
+  if (fminf(lp, fminf(l0, dot3(D, D))) < 1e-24f) m |= 1u << last;
+  return m;
+}
 template <int MAXV, int MINV, bool DEG, bool COMPAT>
-__device__ __forceinline__ void ring_gather(const float4 *sP, const unsigned short (&rn)[MAXV], const unsigned short (&rf)[MAXV], int val,
+__device__ __forceinline__ void ring_gather(const float4 *sP, const unsigned short (&ro)[MAXV], const unsigned short (&rf)[MAXV], int val,
                                             unsigned m, float4 Pv, float3 com, float inv_l0, int stale_from, float3 &T, float3 &g,
                                             float3 &gs) {
   float3 Qp = f3(0.f, 0.f, 0.f), Q0 = f3(0.f, 0.f, 0.f);
@@ -1020,8 +1092,8 @@ __device__ __forceinline__ void ring_gather(const float4 *sP, const unsigned sho
 #pragma unroll
   for (int i = 0; i < MAXV; i++) {
     if (i >= MINV && i >= val) break;
-    rf_last = rf[i];
-    const float4 Pn = sP[rn[i]];
+    if (COMPAT) rf_last = rf[i];
+    const float4 Pn = lds_off(sP, ro[i]);
     const float3 E = sub3(Pn, Pv);
     const float len2 = dot3(E, E);
     const float rl = rsqrt_fast(len2);
@@ -1030,22 +1102,31 @@ __device__ __forceinline__ void ring_gather(const float4 *sP, const unsigned sho
     if (DEG) {
       // edge (v, n_i) belongs to ring faces i-1 and i; each contributes unit(E)*dl unless degenerate
       const int ip = (i == 0) ? val - 1 : i - 1;
-      sc *= (float)(2 - ((m >> (2 * i + 1)) & 1u) - ((m >> (2 * ip + 1)) & 1u));
+      const int w = 2 - (int)((m >> i) & 1u) - (int)((m >> ip) & 1u);
+      sc = (w == 0) ? 0.0f : sc * (float)w;  // an edge of zero length has no direction: both its faces are skipped
     }
     T.x += E.x * sc; T.y += E.y * sc; T.z += E.z * sc;
     const float3 Q = COMPAT ? sub3(Pn, com) : E;
     if (i == 0) Q0 = Q;
-    else {
+    else if (COMPAT) {
       const float3 c = cross3(Qp, Q);  // gradient of ring face i-1 = (v, n_{i-1}, n_i)
       g.x += c.x; g.y += c.y; g.z += c.z;
-      if (COMPAT && (int)rf[i - 1] >= stale_from) { gs.x += c.x; gs.y += c.y; gs.z += c.z; }
+      if ((int)rf[i - 1] >= stale_from) { gs.x += c.x; gs.y += c.y; gs.z += c.z; }
+    } else {  // g += Qp x Q as two chained FMAs per component
+      g.x = fmaf(Qp.y, Q.z, g.x); g.x = fmaf(-Qp.z, Q.y, g.x);
+      g.y = fmaf(Qp.z, Q.x, g.y); g.y = fmaf(-Qp.x, Q.z, g.y);
+      g.z = fmaf(Qp.x, Q.y, g.z); g.z = fmaf(-Qp.y, Q.x, g.z);
     }
     Qp = Q;
   }
-  {
+  if (COMPAT) {
     const float3 c = cross3(Qp, Q0);  // ring face val-1 = (v, n_{val-1}, n_0)
     g.x += c.x; g.y += c.y; g.z += c.z;
-    if (COMPAT && rf_last >= stale_from) { gs.x += c.x; gs.y += c.y; gs.z += c.z; }
+    if (rf_last >= stale_from) { gs.x += c.x; gs.y += c.y; gs.z += c.z; }
+  } else {
+    g.x = fmaf(Qp.y, Q0.z, g.x); g.x = fmaf(-Qp.z, Q0.y, g.x);
+    g.y = fmaf(Qp.z, Q0.x, g.y); g.y = fmaf(-Qp.x, Q0.z, g.y);
+    g.z = fmaf(Qp.x, Q0.y, g.z); g.z = fmaf(-Qp.y, Q0.x, g.z);
   }
   if (!DEG) { T.x *= 2.0f; T.y *= 2.0f; T.z *= 2.0f; }
 }
@@ -1060,23 +1141,22 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
   const int nv = P.nv, nf = P.nf;
   float4 *sP = reinterpret_cast<float4 *>(smem_raw);
   float4 *sF = sP + nv;
-  unsigned char *sFlag = reinterpret_cast<unsigned char *>(sF + step3d_mid_slots(nv, nf));
+  const int nvp = vflag_stride(nv);
+  unsigned char *sVin = reinterpret_cast<unsigned char *>(sF + step3d_mid_slots(nv, nf));  // per-vertex flags of the current positions
+  unsigned char *sVout = sVin + nvp;                                                       // ... of the new positions (face pass below)
   const int tid = threadIdx.x;
   const int ci = blockIdx.x;
   const float4 *gP = P.pos_in + (size_t)ci * nv;
-  const unsigned char *gf = P.flag_in + (size_t)ci * nf;
 
-  // ---- stage the vertex ring and the per-face flags of the current positions (computed by the previous epilogue) ----
-  const bool bulk_flags = (nf & 15) == 0;  // bulk copies move multiples of 16 bytes between 16-byte aligned addresses
+  // ---- stage the vertex ring and the per-vertex flags of the current positions (computed by the previous epilogue) ----
   if (tid == 0) {
     mbar_init(&sBar, 1);
-    const unsigned pb = (unsigned)(sizeof(float4) * nv), fb = bulk_flags ? (unsigned)nf : 0u;
-    mbar_expect_tx(&sBar, pb + fb);
+    const unsigned pb = (unsigned)(sizeof(float4) * nv);
+    mbar_expect_tx(&sBar, pb + (unsigned)nvp);
     bulk_g2s(sP, gP, pb, &sBar);
-    if (bulk_flags) bulk_g2s(sFlag, gf, fb, &sBar);
+    bulk_g2s(sVin, P.flag_in + (size_t)ci * nvp, (unsigned)nvp, &sBar);
   }
-  if (!bulk_flags)
-    for (int f = tid; f < nf; f += STEP_THREADS) sFlag[f] = gf[f];
+  for (int v = tid; v < nvp / 4; v += STEP_THREADS) reinterpret_cast<unsigned *>(sVout)[v] = 0u;
   const float4 cA = P.cellA[ci], cB = P.cellB[ci];
   const float Kv = cA.x, Ka = cA.y, Ks = cA.z, v0 = cA.w, a0 = cB.x, l0 = cB.y;
   const float4 bi2 = P.bnd_in[BND * (size_t)ci + 2], bi3 = P.bnd_in[BND * (size_t)ci + 3];
@@ -1088,45 +1168,51 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
   const float dcoef = (COMPAT && doVol) ? (-Kv * (bi3.z / v0 - 1.0f)) * (1.0f / 6.0f) - coef : 0.0f;
   const bool doArea = (P.mask & DPM3D_AREA) && !(Ka < 1e-8f);
   const bool doStick = (P.mask & DPM3D_STICK) && !(Ks < 1e-12f);
-  __shared__ float sL0;  // handed to the epilogue through shared memory: no register held across the kernel, no global load at its end
-  if (tid == 0) sL0 = l0;
   const float inv_l0 = 1.0f / l0;
   const float scale = doArea ? Ka * sqrtf(a0) / l0 * 0.3f : 0.0f;  // :162
   const bool doRep = (P.mask & DPM3D_REPEL) && P.Kc != 0.0f;
-  __syncthreads();  // the barrier is initialised (and the plain flag copy, if any, is complete)
+  __syncthreads();  // the barrier is initialised
   mbar_wait(&sBar, 0);
 
   // ---- ring pass: every vertex gathers over its constant ring adjacency ---------------------------------
   DPM_UNROLL(DPM_RING_UNROLL)
-  for (int v = tid; v < nv; v += STEP_THREADS) {
+  for (int r = tid; r < nv; r += STEP_THREADS) {
+    const int v = (int)__ldg(P.vorder + r);  // the order the host chose: the 8 lanes of a quarter-warp gather from 8 different bank groups
     const int val = (MINV == MAXV) ? MAXV : (int)__ldg(P.valence + v);
-    // ring tables: 8 x uint16 per vertex = one 16-byte load each (valence <= 8; the stride-16 layout takes two)
-    unsigned short rn[MAXV], rf[MAXV];
+    // ring tables: 8 x uint16 per vertex = one 16-byte load each (valence <= 8; the stride-16 layout takes two); the
+    // neighbour table holds byte offsets into sP; the face table is only needed by the reference-race mode
+    unsigned short ro[MAXV], rf[MAXV];
     {
       const uint4 a = __ldg(reinterpret_cast<const uint4 *>(P.ring_nbr + (size_t)v * P.ring_stride));
-      const uint4 b = __ldg(reinterpret_cast<const uint4 *>(P.ring_face + (size_t)v * P.ring_stride));
-      rn[0] = a.x & 0xffff; rn[1] = a.x >> 16; rn[2] = a.y & 0xffff; rn[3] = a.y >> 16; rn[4] = a.z & 0xffff; rn[5] = a.z >> 16;
-      rf[0] = b.x & 0xffff; rf[1] = b.x >> 16; rf[2] = b.y & 0xffff; rf[3] = b.y >> 16; rf[4] = b.z & 0xffff; rf[5] = b.z >> 16;
-      if (MAXV > 6) { rn[6] = a.w & 0xffff; rn[7] = a.w >> 16; rf[6] = b.w & 0xffff; rf[7] = b.w >> 16; }
+      ro[0] = a.x & 0xffff; ro[1] = a.x >> 16; ro[2] = a.y & 0xffff; ro[3] = a.y >> 16; ro[4] = a.z & 0xffff; ro[5] = a.z >> 16;
+      if (MAXV > 6) { ro[6] = a.w & 0xffff; ro[7] = a.w >> 16; }
       if (MAXV > 8) {
         const uint4 c = __ldg(reinterpret_cast<const uint4 *>(P.ring_nbr + (size_t)v * P.ring_stride) + 1);
-        const uint4 d = __ldg(reinterpret_cast<const uint4 *>(P.ring_face + (size_t)v * P.ring_stride) + 1);
-        rn[MAXV - 8] = c.x & 0xffff; rn[MAXV - 7] = c.x >> 16; rn[MAXV - 6] = c.y & 0xffff; rn[MAXV - 5] = c.y >> 16;
-        rn[MAXV - 4] = c.z & 0xffff; rn[MAXV - 3] = c.z >> 16; rn[MAXV - 2] = c.w & 0xffff; rn[MAXV - 1] = c.w >> 16;
-        rf[MAXV - 8] = d.x & 0xffff; rf[MAXV - 7] = d.x >> 16; rf[MAXV - 6] = d.y & 0xffff; rf[MAXV - 5] = d.y >> 16;
-        rf[MAXV - 4] = d.z & 0xffff; rf[MAXV - 3] = d.z >> 16; rf[MAXV - 2] = d.w & 0xffff; rf[MAXV - 1] = d.w >> 16;
+        ro[MAXV - 8] = c.x & 0xffff; ro[MAXV - 7] = c.x >> 16; ro[MAXV - 6] = c.y & 0xffff; ro[MAXV - 5] = c.y >> 16;
+        ro[MAXV - 4] = c.z & 0xffff; ro[MAXV - 3] = c.z >> 16; ro[MAXV - 2] = c.w & 0xffff; ro[MAXV - 1] = c.w >> 16;
+      }
+#pragma unroll
+      for (int i = 0; i < MAXV; i++) rf[i] = 0;
+      if (COMPAT) {
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(P.ring_face + (size_t)v * P.ring_stride));
+        rf[0] = b.x & 0xffff; rf[1] = b.x >> 16; rf[2] = b.y & 0xffff; rf[3] = b.y >> 16; rf[4] = b.z & 0xffff; rf[5] = b.z >> 16;
+        if (MAXV > 6) { rf[6] = b.w & 0xffff; rf[7] = b.w >> 16; }
+        if (MAXV > 8) {
+          const uint4 d = __ldg(reinterpret_cast<const uint4 *>(P.ring_face + (size_t)v * P.ring_stride) + 1);
+          rf[MAXV - 8] = d.x & 0xffff; rf[MAXV - 7] = d.x >> 16; rf[MAXV - 6] = d.y & 0xffff; rf[MAXV - 5] = d.y >> 16;
+          rf[MAXV - 4] = d.z & 0xffff; rf[MAXV - 3] = d.z >> 16; rf[MAXV - 2] = d.w & 0xffff; rf[MAXV - 1] = d.w >> 16;
+        }
       }
     }
-    unsigned m = 0;
-#pragma unroll
-    for (int i = 0; i < MAXV; i++) if (i < MINV || i < val) m |= (unsigned)sFlag[rf[i]] << (2 * i);
-    const int ndown = __popc(m & 0x55555555u);
+    const unsigned vf = sVin[v];
+    const int ndown = (int)(vf & 0x7fu);
     const float4 Pv = sP[v];
     float3 T = f3(0.f, 0.f, 0.f), g = f3(0.f, 0.f, 0.f), gs = f3(0.f, 0.f, 0.f);
-    if (__any_sync(__activemask(), (m & 0xaaaaaaaau) != 0u))
-      ring_gather<MAXV, MINV, true, COMPAT>(sP, rn, rf, val, m, Pv, com, inv_l0, P.stale_from, T, g, gs);
-    else
-      ring_gather<MAXV, MINV, false, COMPAT>(sP, rn, rf, val, m, Pv, com, inv_l0, P.stale_from, T, g, gs);
+    if (__any_sync(__activemask(), (vf & 0x80u) != 0u)) {
+      const unsigned m = ring_deg_mask<MAXV, MINV>(sP, ro, val, Pv);
+      ring_gather<MAXV, MINV, true, COMPAT>(sP, ro, rf, val, m, Pv, com, inv_l0, P.stale_from, T, g, gs);
+    } else
+      ring_gather<MAXV, MINV, false, COMPAT>(sP, ro, rf, val, 0u, Pv, com, inv_l0, P.stale_from, T, g, gs);
     float3 F = f3(T.x * scale + coef * g.x, T.y * scale + coef * g.y, T.z * scale + coef * g.z);
     if (COMPAT) { F.x += dcoef * gs.x; F.y += dcoef * gs.y; F.z += dcoef * gs.z; }
     if (doStick && ndown > 0) {
@@ -1142,14 +1228,14 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
     }
     sF[v] = make_float4(F.x, F.y, F.z, 0.f);
   }
-  __syncthreads();  // everyone is done reading start-of-step sP
-
   // ---- Euler update (EulerPosition :380), outputs ----------------------------------------------------------
   // The contact weights are the only input from this timestep's units / contact kernels: everything above overlaps them.
+  // Their per-cell counts are requested before the barrier that ends the ring pass, so the load latency hides behind it.
   griddep_wait();
   constexpr bool doAtt = ATT;
   const int ucnt = (doRep || doAtt) ? P.unit_cnt[ci] : 0;
   const int ubase = (doRep || doAtt) ? P.unit_base[ci] : 0;
+  __syncthreads();  // everyone is done reading start-of-step sP
   const float *uw = P.unit_w + ubase;
   const float4 *ua = P.unit_att + ubase;
   // fold the evaluated contact units into the forces of the few vertices that have any (the units kernel's compact list;
@@ -1185,16 +1271,33 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
     }
     __syncthreads();
   }
-  VertPartial vp;
-  vp.init();
-  for (int v = tid; v < nv; v += STEP_THREADS) {
-    const float4 F = sF[v];
-    float4 np = sP[v];
-    np.x += F.x * P.dt; np.y += F.y * P.dt; np.z += F.z * P.dt;
-    np.w = 0.f;
-    if (P.force_out) P.force_out[(size_t)ci * nv + v] = F;
-    sP[v] = np;
-    vp.add(np);
+  // The kernel point of the NEW positions: the serial-order COM of the current ones (known since the prologue).
+  const float3 kp = com;
+  float4 *part = P.part + ((size_t)ci * (STEP_THREADS / 32) + (tid >> 5)) * 3;  // this warp's partial record
+  {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    float r2 = 0.0f;
+    for (int v = tid; v < nv; v += STEP_THREADS) {
+      const float4 F = sF[v];
+      float4 np = sP[v];
+      np.x += F.x * P.dt; np.y += F.y * P.dt; np.z += F.z * P.dt;
+      np.w = 0.f;
+      if (P.force_out) P.force_out[(size_t)ci * nv + v] = F;
+      sP[v] = np;
+      lo[0] = fminf(lo[0], np.x); lo[1] = fminf(lo[1], np.y); lo[2] = fminf(lo[2], np.z);
+      hi[0] = fmaxf(hi[0], np.x); hi[1] = fmaxf(hi[1], np.y); hi[2] = fmaxf(hi[2], np.z);
+      const float3 q = sub3(np, kp);
+      r2 = fmaxf(r2, dot3(q, q));
+    }
+    // the warp's AABB and bounding radius leave now (the group's chain warp folds the partials of the cell's four warps):
+    // no register carries them through the face pass, and no thread of this CTA has to wait for a block-wide reduction
+#pragma unroll
+    for (int d = 0; d < 3; d++) { lo[d] = warp_min(lo[d]); hi[d] = warp_max(hi[d]); }
+    r2 = warp_max(r2);
+    if ((tid & 31) == 0) {
+      part[0] = make_float4(lo[0], lo[1], lo[2], r2);
+      part[1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
   }
   fence_async_smem();  // this thread's sP writes -> visible to the bulk store issued below
   __syncthreads();
@@ -1202,10 +1305,173 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
   griddep_launch();  // the next timestep's rebuild kernel may be scheduled; it waits for this grid's completion before it reads anything
 
   // ---- next step's per-cell scalars from the NEW positions --------------------------------------------------
-  CellTopo T;
-  T.faces = P.faces; T.ring_nbr = P.ring_nbr; T.valence = P.valence; T.ring_stride = P.ring_stride; T.nv = nv; T.nf = nf;
-  cell_scalars(sP, sF, T, vp, bi2.w, &sL0, P.bnd_out + BND * (size_t)ci, P.flag_out + (size_t)ci * nf, P.bbox_lo + ci, P.bbox_hi + ci, P.st);
-  if (tid == 0) bulk_wait_all();  // the bulk store has read sP (and landed) before the CTA's shared memory is released
+  // ONE pass over the faces: signed-volume term dot(cross(P0,P1),P2)/6.0f in the reference's operation order, unfused
+  // (shaders/Cell3D_Kernel.cl:58-61) -> global memory, for the chain warp of this cell's group; star-shape test about the
+  // kernel point; next step's facing-the-substrate (StickToSurface :209-214) and degenerate-edge (:151) flags; longest edge.
+  {
+    float *gTerm = P.terms + (size_t)ci * terms_stride(nf);
+    const float near_z = l0 * 2.0f;
+    int star = 1;
+    float e2 = 0.0f;
+    DPM_UNROLL(DPM_FACE_UNROLL)
+    for (int r = tid; r < nf; r += STEP_THREADS) {
+      const ushort4 fc = __ldg(P.faces_proc + r);  // .w = face id: a warp's 32 faces are a permutation of one aligned block of 32
+      const float4 P0 = sP[fc.x], P1 = sP[fc.y], P2 = sP[fc.z];
+      const float cx = __fsub_rn(__fmul_rn(P0.y, P1.z), __fmul_rn(P0.z, P1.y));
+      const float cy = __fsub_rn(__fmul_rn(P0.z, P1.x), __fmul_rn(P0.x, P1.z));
+      const float cz = __fsub_rn(__fmul_rn(P0.x, P1.y), __fmul_rn(P0.y, P1.x));
+      gTerm[fc.w] = div6_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, P2.x), __fmul_rn(cy, P2.y)), __fmul_rn(cz, P2.z)));
+      const float3 A = sub3(P1, P0), B = sub3(P2, P0), C = sub3(P2, P1);
+      const float3 n = cross3(A, B);
+      const float nn = dot3(n, n);
+      star &= face_sees_centre(P0, n, nn, kp) ? 1 : 0;
+      const bool down = n.z * rsqrt_fast(nn) < -0.1f;
+      const float la = dot3(A, A), lb = dot3(B, B), lc = dot3(C, C);
+      e2 = fmaxf(e2, fmaxf(la, fmaxf(lb, lc)));  // every edge is an edge of some face: longest edge for free
+      if (down) {  // StickToSurface acts on a corner only below the plane or within 2 l0 of it (:226-246): nothing else is counted
+        if (P0.z < near_z) vflag_add(sVout, fc.x, 1u);
+        if (P1.z < near_z) vflag_add(sVout, fc.y, 1u);
+        if (P2.z < near_z) vflag_add(sVout, fc.z, 1u);
+      }
+      if (fminf(la, fminf(lb, lc)) < 1e-24f) { vflag_or(sVout, fc.x, 0x80u); vflag_or(sVout, fc.y, 0x80u); vflag_or(sVout, fc.z, 0x80u); }
+    }
+    e2 = warp_max(e2);
+    star = __all_sync(0xffffffffu, star);
+    if ((tid & 31) == 0) part[2] = make_float4(e2, star ? 1.f : 0.f, 0.f, 0.f);
+    fence_async_smem();  // this thread's flag atomics -> visible to the bulk store issued below
+  }
+  __syncthreads();  // CTA-scope ordering of every thread's global stores (terms, partials) before thread 0's device-wide fence
+  if (tid >= 32) return;  // warps 1..3 are done; warp 0 publishes the cell
+  int last = 0;
+  if (tid == 0) {
+    bulk_s2g(P.flag_out + (size_t)ci * nvp, sVout, (unsigned)nvp);
+    bulk_wait_all();   // the new positions and vertex flags have left shared memory and landed
+    asm volatile("fence.proxy.async;" ::: "memory");  // async-proxy writes (the bulk store) ordered before the release below
+    __threadfence();
+    // publish this cell; the CTA that completes its group evaluates the group's serial chains and assembles its bounds
+    const int grp0 = ci / CHAIN_GROUP;
+    const int prev = atomicAdd(P.grp_done + grp0, 1);
+    last = (prev == min(CHAIN_GROUP, P.nc - grp0 * CHAIN_GROUP) - 1) ? 1 : 0;
+  }
+  if (!__shfl_sync(0xffffffffu, last, 0)) return;
+
+  // ---- serial-order COM (:35-44) and signed volume (:46-64) of the group's cells: ONE warp, lane = (cell, chain) ----
+  // chains 0/1/2 = COM x/y/z (vertex k: pos[k]), chain 3 = volume (terms 2k, 2k+1).  Every iteration is one 8-byte LDS per
+  // lane and two predicated FADDs, as in the single-cell version, but 8 cells share the instruction stream.  The operands
+  // are staged from global memory (L2: written by the group's CTAs just now) by cp.async, CHAIN_STAGES chunks in flight.
+  __threadfence();  // acquire: the other CTAs' positions / terms / bounds
+  asm volatile("fence.proxy.async;" ::: "memory");
+  {
+    const int grp = ci / CHAIN_GROUP;
+    const int gcount = min(CHAIN_GROUP, P.nc - grp * CHAIN_GROUP);
+    if (tid == 0) P.grp_done[grp] = 0;  // ready for the next timestep
+    const int lane = tid, cell = lane >> 2, chain = lane & 3;
+    const bool live = cell < gcount;
+    const int c0 = grp * CHAIN_GROUP;
+    const int tstride = terms_stride(nf);
+    const int niter = max(nv, (nf + 1) >> 1), nchunk = (niter + CHAIN_CH - 1) / CHAIN_CH;
+    const int cnt = !live ? 0 : (chain == 3 ? ((nf + 1) >> 1) : nv);
+    const unsigned sbase = smem_addr(smem_raw);
+    const bool useA = chain != 1, useB = (chain & 1) != 0;
+    const unsigned lane_off = (chain == 3) ? (unsigned)(CHAIN_GROUP * CHAIN_POS_STRIDE + cell * CHAIN_TERM_STRIDE)
+                                           : (unsigned)(cell * CHAIN_POS_STRIDE + (chain == 2 ? 8 : 0));
+    const unsigned lane_step = (chain == 3) ? 8u : 16u;
+    // staging by bulk async copies (TMA unit; they do not occupy the LSU data pipe): lane c copies cell c's chunk of
+    // positions, lane 8 + c its chunk of terms; one mbarrier per stage counts the bytes
+    __shared__ __align__(8) unsigned long long sBarC[CHAIN_STAGES];
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < CHAIN_STAGES; q++) mbar_init(&sBarC[q], 1);
+    }
+    __syncwarp();
+    auto stage_chunk = [&](int ch) {
+      if (ch < nchunk) {
+        const int stg = ch % CHAIN_STAGES;
+        unsigned char *st = smem_raw + stg * CHAIN_STAGE_BYTES;
+        const int k0 = ch * CHAIN_CH;
+        const unsigned pbytes = (unsigned)(16 * max(0, min(CHAIN_CH, nv - k0)));
+        const unsigned tbytes = (2 * k0 < tstride) ? (unsigned)(8 * CHAIN_CH) : 0u;
+        if (lane == 0) mbar_expect_tx(&sBarC[stg], (unsigned)gcount * (pbytes + tbytes));
+        __syncwarp();
+        if (lane < CHAIN_GROUP) {
+          if (lane < gcount && pbytes) bulk_g2s(st + lane * CHAIN_POS_STRIDE, P.pos_out + (size_t)(c0 + lane) * nv + k0, pbytes, &sBarC[stg]);
+        } else if (lane < 2 * CHAIN_GROUP) {
+          const int c = lane - CHAIN_GROUP;
+          if (c < gcount && tbytes)
+            bulk_g2s(st + CHAIN_GROUP * CHAIN_POS_STRIDE + c * CHAIN_TERM_STRIDE, P.terms + (size_t)(c0 + c) * tstride + 2 * k0, tbytes, &sBarC[stg]);
+        }
+      }
+    };
+#pragma unroll
+    for (int c = 0; c < CHAIN_STAGES - 1; c++) stage_chunk(c);
+    float sacc = 0.0f;
+    for (int ch = 0; ch < nchunk; ch++) {
+      stage_chunk(ch + CHAIN_STAGES - 1);
+      mbar_wait(&sBarC[ch % CHAIN_STAGES], (unsigned)((ch / CHAIN_STAGES) & 1));
+      const int k0 = ch * CHAIN_CH;
+      unsigned addr = sbase + (unsigned)((ch % CHAIN_STAGES) * CHAIN_STAGE_BYTES) + lane_off;
+      if (__all_sync(0xffffffffu, !live || k0 + CHAIN_CH <= cnt)) {
+        if (live) {
+#pragma unroll
+          for (int q = 0; q < CHAIN_CH; q += 8, addr += 8u * lane_step) {
+            float2 t[8];
+            if (chain == 3) {
+              t[0] = lds_v2<0>(addr); t[1] = lds_v2<8>(addr); t[2] = lds_v2<16>(addr); t[3] = lds_v2<24>(addr);
+              t[4] = lds_v2<32>(addr); t[5] = lds_v2<40>(addr); t[6] = lds_v2<48>(addr); t[7] = lds_v2<56>(addr);
+            } else {
+              t[0] = lds_v2<0>(addr); t[1] = lds_v2<16>(addr); t[2] = lds_v2<32>(addr); t[3] = lds_v2<48>(addr);
+              t[4] = lds_v2<64>(addr); t[5] = lds_v2<80>(addr); t[6] = lds_v2<96>(addr); t[7] = lds_v2<112>(addr);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              if (useA) sacc = __fadd_rn(sacc, t[j].x);
+              if (useB) sacc = __fadd_rn(sacc, t[j].y);
+            }
+          }
+        }
+      } else {
+        for (int q = 0; q < CHAIN_CH; q++, addr += lane_step) {
+          if (k0 + q < cnt) {
+            const float2 t = lds_v2<0>(addr);
+            if (useA) sacc = __fadd_rn(sacc, t.x);
+            if (useB && !(chain == 3 && 2 * (k0 + q) + 1 >= nf)) sacc = __fadd_rn(sacc, t.y);
+          }
+        }
+      }
+      __syncwarp();  // every lane is done with this stage before it is refilled
+    }
+    const float res = (chain == 3) ? fabsf(sacc) : __fmul_rn(sacc, __fdiv_rn(1.0f, (float)nv));
+    const int b = lane & ~3;
+    const float cx = __shfl_sync(0xffffffffu, res, b), cy = __shfl_sync(0xffffffffu, res, b + 1), cz = __shfl_sync(0xffffffffu, res, b + 2),
+                vol = __shfl_sync(0xffffffffu, res, b + 3);
+    if (live && chain == 0) {  // one lane per cell: fold the four warps' partials and write the cell's bounds record
+      const int cc = c0 + cell;
+      const float4 *pr = P.part + (size_t)cc * (STEP_THREADS / 32) * 3;
+      float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY}, rr = 0.f, em = 0.f;
+      bool st = true;
+#pragma unroll
+      for (int w = 0; w < STEP_THREADS / 32; w++) {
+        const float4 a = __ldcg(pr + 3 * w), b2 = __ldcg(pr + 3 * w + 1), c2 = __ldcg(pr + 3 * w + 2);
+        l[0] = fminf(l[0], a.x); l[1] = fminf(l[1], a.y); l[2] = fminf(l[2], a.z); rr = fmaxf(rr, a.w);
+        h[0] = fmaxf(h[0], b2.x); h[1] = fmaxf(h[1], b2.y); h[2] = fmaxf(h[2], b2.z);
+        em = fmaxf(em, c2.x); st = st && c2.y != 0.0f;
+      }
+      const float pad = CONTACT_PAD * sqrtf(em);
+      const float4 old2 = P.bnd_in[BND * (size_t)cc + 2];  // (COM, volume) of the positions this timestep started from
+      float4 *bnd_cell = P.bnd_out + BND * (size_t)cc;
+      bnd_cell[0] = make_float4(l[0], l[1], l[2], rr);
+      bnd_cell[1] = make_float4(h[0], h[1], h[2], pad);
+      bnd_cell[2] = make_float4(cx, cy, cz, vol);
+      // previous volume (compat mode only); l0 travels with the bounds (ghost cells have no parameters)
+      bnd_cell[3] = make_float4(0.f, st ? 1.f : 0.f, old2.w, P.cellB[cc].y);
+      bnd_cell[4] = make_float4(old2.x, old2.y, old2.z, 0.f);  // kernel point of the new positions
+      {  // neighbour-list validity
+        const float4 bl = P.bbox_lo[cc], bh = P.bbox_hi[cc];
+        if (l[0] < bl.x || l[1] < bl.y || l[2] < bl.z || h[0] > bh.x || h[1] > bh.y || h[2] > bh.z) P.st->rebuild = 1;
+        if (pad > P.st->range) P.st->rebuild = 1;  // the candidate lists were built for smaller contact pads
+      }
+    }
+  }
 }
 
 }  // namespace dpm

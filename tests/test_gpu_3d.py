@@ -255,6 +255,39 @@ def test_vertex_exactly_on_a_neighbour_vertex():
     h.close()
 
 
+@pytest.mark.parametrize("mask", [2, 15])
+def test_degenerate_edges_skip_their_faces(mask):
+    """SurfaceAreaForceUpdate drops a whole face when one of its edges is shorter than 1e-12 (shaders/Cell3D_Kernel.cl:151).
+    Two edges of cell 0 and one of cell 3 are collapsed to zero length: the step kernel finds the affected vertices through
+    the per-vertex flags of the previous epilogue (here: the bounds kernel of the upload) and weights every ring edge by the
+    number of its non-degenerate faces; all forces must stay finite and equal the oracle's."""
+    O = _oracle()
+    d = H.config_test3d_cpp()
+    nv = d["nv"]
+    V = d["verts"].copy().reshape(d["nc"], nv, 4)
+    f = d["faces"]
+    V[0, f[10, 1]] = V[0, f[10, 0]]      # an edge of face 10 of cell 0
+    V[0, f[200, 2]] = V[0, f[200, 1]]    # ... and of face 200
+    V[3, f[77, 0]] = V[3, f[77, 2]]
+    V = V.reshape(-1, 4)
+    h = _handle(d)
+    V1, F = _gpu_step(h, d, V, 1, mask)
+    args = (V, d["faces"], *[d[k] for k in PKEYS], d["Kre"], d["PBC"], d["L"])
+    Fref = O.forces3d(*args, which=mask)
+    Fref64 = O.forces3d(*args, which=mask, dtype=np.float64)
+    assert np.isfinite(F).all() and np.isfinite(Fref).all() and np.isfinite(V1).all()
+    H.assert_forces_close(F[:, :3], Fref[:, :3], Fref64[:, :3], what="forces with degenerate edges")
+    # a second step from the GPU's own state: the flags now come from the step kernel's face pass
+    h.step(1, float(d["dt"]), float(d["Kre"]), 0.0, d["PBC"], float(d["L"]))
+    V2, F2 = h.download()
+    args1 = (V1, d["faces"], *[d[k] for k in PKEYS], d["Kre"], d["PBC"], d["L"])
+    Fr1 = O.forces3d(*args1, which=mask)
+    Fr164 = O.forces3d(*args1, which=mask, dtype=np.float64)
+    assert np.isfinite(F2).all()
+    H.assert_forces_close(F2[:, :3], Fr1[:, :3], Fr164[:, :3], what="second step with degenerate edges")
+    h.close()
+
+
 def test_cldpm_tissue3d_with_642_vertex_cells():
     """Extension: the subdivision level through the drop-in classes.  9 cells of the 642-vertex mesh
     (Cell3D(start, calA, r0, 3)) through Tissue3D.CLEulerUpdate vs the all-pairs oracle on the same flat arrays."""
