@@ -104,9 +104,19 @@ constexpr int BND = 5;              // float4 per cell in the bounds arrays:
 // positions one timestep earlier; after an upload the COM itself): the centre of the bounding sphere, the apex of the
 // star-shape test and the point the contact kernel walks from.  Nothing of the step kernel's epilogue therefore waits for
 // the serial COM / volume chains of the NEW positions; those only feed the next timestep (shift, force direction, strain).
-constexpr int CHAIN_GROUP = 8;      // cells whose serial chains one warp evaluates together (4 chains per cell = 32 lanes)
+#ifndef DPM_CHAIN_GROUP
+#define DPM_CHAIN_GROUP 8
+#endif
+#ifndef DPM_CHAIN_STAGES
+#define DPM_CHAIN_STAGES 3
+#endif
+#ifndef DPM_CHAIN_BULK
+#define DPM_CHAIN_BULK 0  // 0: per-lane cp.async (LDGSTS) staging of the chain operands; 1: bulk async copies (TMA unit) — measured 6 % slower
+                          // per timestep on config D: its latency per chunk is longer and the chains of the last groups are the kernel's tail
+#endif
+constexpr int CHAIN_GROUP = DPM_CHAIN_GROUP;  // cells whose serial chains one warp evaluates together (4 chains per cell)
 constexpr int CHAIN_CH = 32;        // chain iterations staged per chunk
-constexpr int CHAIN_STAGES = 3;     // chunks in flight (cp.async groups)
+constexpr int CHAIN_STAGES = DPM_CHAIN_STAGES;  // chunks in flight
 constexpr int CHAIN_POS_STRIDE = CHAIN_CH * 16 + 16;  // bytes per cell and stage, padded: the 8 cells' lanes hit 8 different bank quads
 constexpr int CHAIN_TERM_STRIDE = CHAIN_CH * 8 + 16;
 constexpr int CHAIN_STAGE_BYTES = CHAIN_GROUP * (CHAIN_POS_STRIDE + CHAIN_TERM_STRIDE);
@@ -1376,6 +1386,7 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
     const unsigned lane_off = (chain == 3) ? (unsigned)(CHAIN_GROUP * CHAIN_POS_STRIDE + cell * CHAIN_TERM_STRIDE)
                                            : (unsigned)(cell * CHAIN_POS_STRIDE + (chain == 2 ? 8 : 0));
     const unsigned lane_step = (chain == 3) ? 8u : 16u;
+#if DPM_CHAIN_BULK
     // staging by bulk async copies (TMA unit; they do not occupy the LSU data pipe): lane c copies cell c's chunk of
     // positions, lane 8 + c its chunk of terms; one mbarrier per stage counts the bytes
     __shared__ __align__(8) unsigned long long sBarC[CHAIN_STAGES];
@@ -1408,6 +1419,39 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
     for (int ch = 0; ch < nchunk; ch++) {
       stage_chunk(ch + CHAIN_STAGES - 1);
       mbar_wait(&sBarC[ch % CHAIN_STAGES], (unsigned)((ch / CHAIN_STAGES) & 1));
+#else
+    auto stage_chunk = [&](int ch) {
+      if (ch < nchunk) {
+        const unsigned st = sbase + (unsigned)((ch % CHAIN_STAGES) * CHAIN_STAGE_BYTES);
+        const int k0 = ch * CHAIN_CH;
+#pragma unroll
+        for (int c = 0; c < CHAIN_GROUP; c++) {  // positions: one float4 per lane and cell
+          if (c < gcount && k0 + lane < nv) {
+            const float4 *src = P.pos_out + (size_t)(c0 + c) * nv + k0 + lane;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + (unsigned)(c * CHAIN_POS_STRIDE + lane * 16)), "l"(src) : "memory");
+          }
+        }
+        if (2 * k0 < tstride) {
+#pragma unroll
+          for (int c2 = 0; c2 < CHAIN_GROUP; c2 += 2) {  // terms: 2 * CHAIN_CH floats = 16 float4 per cell, two cells per pass
+            const int c = c2 + (lane >> 4), q = lane & 15;
+            if (c < gcount) {
+              const float *src = P.terms + (size_t)(c0 + c) * tstride + 2 * k0 + 4 * q;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + (unsigned)(CHAIN_GROUP * CHAIN_POS_STRIDE + c * CHAIN_TERM_STRIDE + q * 16)), "l"(src) : "memory");
+            }
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");  // (possibly empty) group: keeps the wait counts uniform
+    };
+#pragma unroll
+    for (int c = 0; c < CHAIN_STAGES - 1; c++) stage_chunk(c);
+    float sacc = 0.0f;
+    for (int ch = 0; ch < nchunk; ch++) {
+      stage_chunk(ch + CHAIN_STAGES - 1);
+      asm volatile("cp.async.wait_group %0;" ::"n"(CHAIN_STAGES - 1) : "memory");
+      __syncwarp();
+#endif
       const int k0 = ch * CHAIN_CH;
       unsigned addr = sbase + (unsigned)((ch % CHAIN_STAGES) * CHAIN_STAGE_BYTES) + lane_off;
       if (__all_sync(0xffffffffu, !live || k0 + CHAIN_CH <= cnt)) {
