@@ -593,6 +593,7 @@ static int upload_common(dpm3d_t *h, const float *verts4, bool on_device, const 
   DPM_CUDA_TRY(cudaGetLastError());
   h->stats.launches += 1;
   h->stats.steps = 0; h->stats.rebuilds = 0; h->stats.contact_evals = 0; h->stats.halo_bytes = 0;  // per-upload counters (launches stay cumulative)
+  if (h->nranks > 1) shard_reset_counters(h);
   // mark the neighbour lists stale
   static const int one = 1;
   DPM_CUDA_TRY(cudaMemcpyAsync(&h->st->rebuild, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));

@@ -78,6 +78,12 @@ struct dpm3d_ctx {
   unsigned char *sendbuf[2] = {nullptr, nullptr}, *recvbuf[2] = {nullptr, nullptr};
   int *sendlist[2] = {nullptr, nullptr};
   size_t msg_bytes = 0;
+  // peer-memory halo path (dpm_halo.cu): this rank's inbox, the peers' inboxes mapped through CUDA IPC, the exchange epoch
+  unsigned char *inbox = nullptr;
+  unsigned char *peer_inbox[64] = {};
+  size_t inbox_bytes = 0;
+  int halo_epoch = 0;
+  bool halo_p2p = false;
 };
 
 namespace dpm {
@@ -85,6 +91,7 @@ namespace dpm {
 int shard_exchange(dpm3d_ctx *h, int pbc, float L);
 int shard_check(dpm3d_ctx *h);   // after a sync: sharding errors (ghost overflow, slabs too thin)
 void shard_free(dpm3d_ctx *h);
+void shard_reset_counters(dpm3d_ctx *h);  // per-upload statistics
 }  // namespace dpm
 
 

@@ -440,73 +440,100 @@ __device__ __forceinline__ int winding_fast(const Step3DParams &P, bool active, 
 // patches, instead of all nf faces with three normalisations and an atan2 each (winding_literal).
 // Returns true if p coincides with a vertex of the neighbour (the caller takes the literal sum: normalize(0) = 0).
 constexpr int PATCH_F = 16;  // faces per patch: 2 per lane of a unit group
-static __device__ __noinline__ bool winding_patches(const ushort4 *__restrict__ faces, int nf, int npatch, const float4 *__restrict__ Vj,
-                                                    const float4 *__restrict__ box, float4 sh, float4 p, float rho, float &w_out, int g,
-                                                    int gshift, unsigned gmask) {
-  const float psx = p.x - sh.x, psy = p.y - sh.y, psz = p.z - sh.z;  // the boxes are those of the unshifted neighbour
-  const float eps = 1e-5f * (fmaxf(fabsf(psx), fmaxf(fabsf(psy), fabsf(psz))) + fmaxf(fabsf(sh.x), fmaxf(fabsf(sh.y), fabsf(sh.z))) + 1.0f);
-  const float reach = rho * 1.01f + eps;
+// Warp-uniform like winding_fast: the warp's 4 groups hold 4 units and advance in lockstep (full-mask votes; a vote with a
+// partial mask in divergent code costs a convergence barrier each time: 27 % of this function's stall samples before).
+// `active` = this lane's group has a unit whose neighbour is not star-shaped.  The ray runs along z, away from the
+// neighbour's kernel point: a vertex beside or outside the neighbour (the usual unit) then meets few or no patches, and
+// outside the neighbour's exact bounding box W = 0 without any test.
+static __device__ __noinline__ bool winding_patches(const ushort4 *__restrict__ faces, int nf, int npatch, bool active,
+                                                    const float4 *__restrict__ Vj, const float4 *__restrict__ box, float4 sh, float4 p,
+                                                    float kz, float4 blo, float4 bhi, float rho, float &w_out, int g, int gshift) {
+  const unsigned FULL = 0xffffffffu;
+  // kz: z of the neighbour's kernel point (shifted), blo / bhi: its exact bounding box (unshifted)
+  const float3 ps = f3(p.x - sh.x, p.y - sh.y, p.z - sh.z);  // the boxes are those of the unshifted neighbour
+  const float eps = 1e-5f * (fmaxf(fabsf(ps.x), fmaxf(fabsf(ps.y), fabsf(ps.z))) + fmaxf(fabsf(sh.x), fmaxf(fabsf(sh.y), fabsf(sh.z))) + 1.0f);
+  const float reach = rho * 1.01f + eps, reach2 = reach * reach;
+  const bool up = p.z >= kz;
+  const bool inbox = active && ps.x >= blo.x - eps && ps.x <= bhi.x + eps && ps.y >= blo.y - eps && ps.y <= bhi.y + eps &&
+                     ps.z >= blo.z - eps && ps.z <= bhi.z + eps;
+  // ---- 1. every lane classifies its patches (independent loads, no votes): bit it <=> patch it * 8 + g ------------------
+  unsigned raybits = 0u, nearbits = 0u;
+  const int nit = (npatch + UNIT_LANES - 1) / UNIT_LANES;
+  if (active) {
+#pragma unroll 4
+    for (int it = 0; it < nit; it++) {
+      const int k = it * UNIT_LANES + g;
+      if (k < npatch) {
+        const float4 lo = __ldg(box + 2 * k), hi = __ldg(box + 2 * k + 1);
+        const bool ray = inbox && ps.x >= lo.x - eps && ps.x <= hi.x + eps && ps.y >= lo.y - eps && ps.y <= hi.y + eps &&
+                         (up ? ps.z <= hi.z + eps : ps.z >= lo.z - eps);
+        const float dx = fmaxf(fmaxf(lo.x - ps.x, ps.x - hi.x), 0.0f), dy = fmaxf(fmaxf(lo.y - ps.y, ps.y - hi.y), 0.0f),
+                    dz = fmaxf(fmaxf(lo.z - ps.z, ps.z - hi.z), 0.0f);
+        const bool near = dx * dx + dy * dy + dz * dz <= reach2;
+        raybits |= (ray ? 1u : 0u) << it;
+        nearbits |= (near ? 1u : 0u) << it;
+      }
+    }
+  }
+  // ---- 2. the faces of the flagged patches, 2 per lane; every group pops its own patches, the warp stays in lockstep ----
   int W = 0;
   float corr = 0.0f;
   bool coincident = false;
-  for (int base = 0; base < npatch; base += UNIT_LANES) {
-    const int k = base + g;
-    bool ray = false, near = false;
-    if (k < npatch) {
-      const float4 lo = __ldg(box + 2 * k), hi = __ldg(box + 2 * k + 1);
-      ray = psx >= lo.x - eps && psx <= hi.x + eps && psy >= lo.y - eps && psy <= hi.y + eps && psz <= hi.z + eps;
-      const float dx = fmaxf(fmaxf(lo.x - psx, psx - hi.x), 0.0f), dy = fmaxf(fmaxf(lo.y - psy, psy - hi.y), 0.0f),
-                  dz = fmaxf(fmaxf(lo.z - psz, psz - hi.z), 0.0f);
-      near = dx * dx + dy * dy + dz * dz <= reach * reach;
-    }
-    const unsigned mn = (__ballot_sync(gmask, near) >> gshift) & 0xffu;
-    unsigned m = ((__ballot_sync(gmask, ray) >> gshift) & 0xffu) | mn;
-    while (m) {  // group-uniform
-      const int j = __ffs(m) - 1;
+  for (int it = 0; it < nit; it++) {
+    const unsigned mn = (__ballot_sync(FULL, (nearbits >> it) & 1u) >> gshift) & 0xffu;
+    unsigned m = ((__ballot_sync(FULL, (raybits >> it) & 1u) >> gshift) & 0xffu) | mn;
+    while (__any_sync(FULL, m != 0u)) {
+      const bool has = m != 0u;
+      const int j = has ? __ffs(m) - 1 : 0;
       m &= m - 1;
-      const bool nearp = (mn >> j) & 1u;
+      const bool nearp = has && ((mn >> j) & 1u);
 #pragma unroll
       for (int hf = 0; hf < PATCH_F / UNIT_LANES; hf++) {
-        const int f = (base + j) * PATCH_F + hf * UNIT_LANES + g;
-        if (f >= nf) continue;
+        const int f = (it * UNIT_LANES + j) * PATCH_F + hf * UNIT_LANES + g;
+        if (!has || f >= nf) continue;
         const ushort4 fc = __ldg(faces + f);
         const float4 q0 = __ldg(Vj + fc.x), q1 = __ldg(Vj + fc.y), q2 = __ldg(Vj + fc.z);
         const float3 a = f3((q0.x + sh.x) - p.x, (q0.y + sh.y) - p.y, (q0.z + sh.z) - p.z);  // reference: V + shift - p
         const float3 b = f3((q1.x + sh.x) - p.x, (q1.y + sh.y) - p.y, (q1.z + sh.z) - p.z);
         const float3 c = f3((q2.x + sh.x) - p.x, (q2.y + sh.y) - p.y, (q2.z + sh.z) - p.z);
-        // edge functions of the projection, exactly antisymmetric under swapping the end points
+        // edge functions of the projection on z = 0, exactly antisymmetric under swapping the end points
         const float eab = __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x));
         const float ebc = __fsub_rn(__fmul_rn(b.x, c.y), __fmul_rn(b.y, c.x));
         const float eca = __fsub_rn(__fmul_rn(c.x, a.y), __fmul_rn(c.y, a.x));
         const bool pab = eab > 0.0f || (eab == 0.0f && fc.x < fc.y), pbc = ebc > 0.0f || (ebc == 0.0f && fc.y < fc.z),
                    pca = eca > 0.0f || (eca == 0.0f && fc.z < fc.x);
         const bool ccw = pab && pbc && pca, cw = !pab && !pbc && !pca;
-        double t = (double)(a.x * (b.y * c.z - b.z * c.y) + a.y * (b.z * c.x - b.x * c.z) + a.z * (b.x * c.y - b.y * c.x));
+        float tf = a.x * (b.y * c.z - b.z * c.y) + a.y * (b.z * c.x - b.x * c.z) + a.z * (b.x * c.y - b.y * c.x);
         if (nearp) {
           float den, num;
           solid_angle_terms(a, b, c, den, num);
           if (den < 1e-8f) {  // skipped by the reference (:293-295)
             double den64, num64;
             solid_angle_terms_f64(a, b, c, den64, num64);
-            t = num64;
+            tf = num64 > 0.0 ? 1.0f : (num64 < 0.0 ? -1.0f : 0.0f);  // the crossing uses the sign the skipped solid angle has
             const double mm = fmax(fabs(num64), fabs(den64));
             if (mm > 0.0) corr += 2.0f * atan2f((float)(num64 / mm), (float)(den64 / mm));
           }
           coincident = coincident || dot3(a, a) == 0.0f || dot3(b, b) == 0.0f || dot3(c, c) == 0.0f;
         }
-        // crossing point above p  <=>  the triple product has the sign of the projected area
-        if (ccw && t > 0.0) W += 1;   // the ray leaves through a face whose normal points up
-        if (cw && t < 0.0) W -= 1;    // the ray enters
+        // the triple product has the sign of the projected area <=> the crossing point lies above p
+        if (up) {
+          if (ccw && tf > 0.0f) W += 1;   // the ray leaves through a face whose normal points up
+          if (cw && tf < 0.0f) W -= 1;    // the ray enters
+        } else {
+          if (cw && tf > 0.0f) W += 1;
+          if (ccw && tf < 0.0f) W -= 1;
+        }
       }
     }
   }
 #pragma unroll
   for (int o = UNIT_LANES / 2; o > 0; o >>= 1) {
-    W += __shfl_xor_sync(gmask, W, o);
-    corr += __shfl_xor_sync(gmask, corr, o);
+    W += __shfl_xor_sync(FULL, W, o);
+    corr += __shfl_xor_sync(FULL, corr, o);
   }
   w_out = (float)W - corr / (4.0f * 3.14159274101257f);
-  return ((__ballot_sync(gmask, coincident) >> gshift) & 0xffu) != 0u;
+  return ((__ballot_sync(FULL, coincident) >> gshift) & 0xffu) != 0u;
 }
 
 // Bounding boxes of the face patches of one cell (not star-shaped): 8 lanes per patch, 2 faces each; exact fp32 min / max.
@@ -771,10 +798,17 @@ __global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(Step3DPa
     }
     float w = 0.0f;
     int why = winding_fast(P, contact && star, Vj, sh, p, f3(bj4.x + sh.x, bj4.y + sh.y, bj4.z + sh.z), bj1.w, w, g, gshift);
-    if (contact && !star) {  // group-uniform branch: the general evaluation over the neighbour's patch boxes
-      const bool coincident = winding_patches(P.faces, P.nf, P.npatch, Vj, P.patch_box + (size_t)cj * P.npatch * 2, sh, p, bj1.w, w, g, gshift, gmask);
-      why = coincident ? 1 : 0;
-      if (g == 0) atomicAdd(&P.st->fallback_why[0], 1ull);  // statistics: units of non-star-shaped neighbours
+    const bool nonstar = contact && !star;
+    if (__any_sync(0xffffffffu, nonstar)) {  // warp-uniform: the general evaluation over the neighbours' patch boxes
+      const float4 bj0 = P.bnd_in[BND * (size_t)cj];
+      float wp = 0.0f;
+      const bool coincident = winding_patches(P.faces, P.nf, P.npatch, nonstar, Vj, P.patch_box + (size_t)cj * P.npatch * 2, sh, p,
+                                              bj4.z + sh.z, bj0, bj1, bj1.w, wp, g, gshift);
+      if (nonstar) {
+        w = wp;
+        why = coincident ? 1 : 0;
+        if (g == 0) atomicAdd(&P.st->fallback_why[0], 1ull);  // statistics: units of non-star-shaped neighbours
+      }
     }
     if (contact && why != 0) {  // group-uniform branch
       w = winding_literal(Vj, P.faces, P.nf, sh, p, g, gmask);

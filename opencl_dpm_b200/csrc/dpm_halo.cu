@@ -20,6 +20,22 @@
 //
 // NCCL is resolved at run time (dlopen "libnccl.so.2"): a single-GPU user needs no NCCL at all, and inside a
 // torch process the already-loaded library is reused.
+//
+// Round 2: the per-step data path no longer goes through NCCL calls.  At shard_init every rank allocates one "inbox" (two
+// message buffers per neighbouring slab, arrival flags, a mailbox of per-rank summaries), the CUDA IPC handles are
+// all-gathered over the NCCL communicator ONCE, and every rank maps its peers' inboxes (NVLink / NVSwitch peer memory).
+// Per timestep:
+//   1. shard_prepare_kernel   as before
+//   2. shard_mailbox_kernel   stores the rank's 8-float summary into every peer's mailbox and waits for theirs (replaces
+//                             the ncclAllGather: one tiny kernel, ~2 NVLink round trips instead of a collective launch)
+//   3. shard_select_kernel    as before, on rebuild only
+//   4. shard_push_kernel      gathers the listed cells and stores them DIRECTLY into the peer's inbox over NVLink — the
+//                             actual count of cells, not the capacity — then releases an arrival flag (count, epoch)
+//   5. shard_unpack_kernel    acquires the flags of its inbox and appends the ghosts behind the owned cells
+// Inboxes and mailboxes are double-buffered by the parity of the exchange epoch: a rank can be at most one exchange ahead
+// of a neighbour (it needs that neighbour's ghosts of the previous timestep), so a buffer is never overwritten before it
+// has been consumed.  All waits are bounded (a peer that died turns into error 3 instead of a hung GPU).
+// DPM_HALO_NCCL=1 selects the round-1 path (ncclAllGather + ncclSend/ncclRecv of capacity-sized messages).
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -40,11 +56,43 @@ struct ShardDev {
   int n_total;  // owned + ghosts (MUST stay the first member: the rebuild kernel reads it as an int*)
   int n_ghost;
   int send_count[2];
-  int error;  // 1: a peer message overflowed the ghost capacity; 2: a cell reaches beyond the adjacent slabs
+  int error;  // 1: a peer message overflowed the ghost capacity; 2: a cell reaches beyond the adjacent slabs; 3: a peer never answered
   int rebuilds_global;
   float margin;
-  int pad;
+  unsigned push_ticket[2];  // CTAs of the push kernel that have stored their cell (per peer; self-resetting)
+  unsigned long long sent_bytes;
 };
+
+// One rank's inbox (peer-mapped by its neighbours).  msg[parity][side]: message from the neighbour on that side;
+// flag[parity][side] = (epoch, count) released by the sender's last CTA; mail[parity][rank][GATHER] + mail_epoch[parity][rank].
+struct InboxLayout {
+  size_t msg_bytes, off_flag, off_mail, off_mail_epoch, total;
+  __host__ __device__ size_t msg(int parity, int side) const { return (size_t)(parity * 2 + side) * msg_bytes; }
+};
+static InboxLayout inbox_layout(size_t msg_bytes, int nranks) {
+  InboxLayout L;
+  L.msg_bytes = (msg_bytes + 255) & ~(size_t)255;
+  L.off_flag = 4 * L.msg_bytes;
+  L.off_mail = L.off_flag + 256;
+  L.off_mail_epoch = L.off_mail + sizeof(float) * GATHER * 2 * (size_t)nranks;
+  L.total = L.off_mail_epoch + sizeof(int) * 2 * (size_t)nranks + 256;
+  return L;
+}
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// bounded wait: ~2 s at 2 GHz; a peer that never answers becomes an error flag, not a hung GPU
+__device__ __forceinline__ bool wait_epoch(const int *p, int epoch) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(p) != epoch) {
+    if (clock64() - t0 > 4000000000ll) return false;
+    __nanosleep(64);
+  }
+  return true;
+}
 
 struct Nccl {
   void *lib = nullptr;
@@ -224,6 +272,85 @@ __global__ void shard_unpack_kernel(float4 *pos, float4 *bnd, int *gid, ShardDev
   for (int v = threadIdx.x; v < nv; v += blockDim.x) dst[v] = src[v];
 }
 
+// ---- 2'. mailbox: the rank's summary goes to every peer, theirs are awaited (replaces the ncclAllGather) ---------------
+struct PeerPtrs { unsigned char *inbox[MAXR]; };
+__global__ void shard_mailbox_kernel(const float *mine, float *all, PeerPtrs peers, unsigned char *my_inbox, InboxLayout L, int rank, int nranks,
+                                     int epoch, ShardDev *sd) {
+  const int r = threadIdx.x, par = epoch & 1;
+  if (r < nranks) {
+    float *dst = reinterpret_cast<float *>(peers.inbox[r] + L.off_mail) + ((size_t)par * nranks + rank) * GATHER;
+#pragma unroll
+    for (int k = 0; k < GATHER; k++) dst[k] = mine[k];
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<int *>(peers.inbox[r] + L.off_mail_epoch) + par * nranks + rank, epoch);
+    // ... and wait for rank r's summary in my own mailbox
+    const bool ok = wait_epoch(reinterpret_cast<const int *>(my_inbox + L.off_mail_epoch) + par * nranks + r, epoch);
+    if (!ok) sd->error = 3;
+    const volatile float *src = reinterpret_cast<const volatile float *>(my_inbox + L.off_mail) + ((size_t)par * nranks + r) * GATHER;
+#pragma unroll
+    for (int k = 0; k < GATHER; k++) all[r * GATHER + k] = src[k];
+  }
+}
+
+// ---- 4'. push: one CTA per (peer, slot) stores its cell straight into the peer's inbox over NVLink ----------------------
+__global__ void shard_push_kernel(const float4 *pos, const float4 *bnd, const int *gid, ShardDev *sd, const int *list0, const int *list1,
+                                  unsigned char *dst0, unsigned char *dst1, int *flag0, int *flag1, int cap, int nv, int epoch) {
+  const int p = blockIdx.x / cap, s = blockIdx.x % cap;
+  unsigned char *buf = p == 0 ? dst0 : dst1;
+  const int cnt = sd->send_count[p];
+  if (s < cnt) {
+    const int c = (p == 0 ? list0 : list1)[s];
+    if (threadIdx.x == 0) reinterpret_cast<int *>(buf + msg_off_gid())[s] = gid[c];
+    if (threadIdx.x < BND) reinterpret_cast<float4 *>(buf + msg_off_bnd(cap))[BND * s + threadIdx.x] = bnd[BND * (size_t)c + threadIdx.x];
+    float4 *dst = reinterpret_cast<float4 *>(buf + msg_off_pos(cap)) + (size_t)s * nv;
+    const float4 *src = pos + (size_t)c * nv;
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) dst[v] = src[v];
+  }
+  // the last CTA of this peer to finish releases the arrival flag (count first, epoch last)
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(&sd->push_ticket[p], 1u);
+    if (done == (unsigned)cap - 1u) {
+      sd->push_ticket[p] = 0u;
+      __threadfence_system();
+      int *flag = p == 0 ? flag0 : flag1;
+      flag[1] = cnt;
+      __threadfence_system();
+      st_release_sys(flag, epoch);
+      sd->sent_bytes += (unsigned long long)cnt * (sizeof(int) + sizeof(float4) * (BND + (size_t)nv)) + 8ull;
+    }
+  }
+}
+
+// ---- 6'. unpack out of the own inbox: waits for the senders' flags ------------------------------------------------------
+__global__ void shard_unpack_p2p_kernel(float4 *pos, float4 *bnd, int *gid, ShardDev *sd, const unsigned char *buf0, const unsigned char *buf1,
+                                        const int *flag0, const int *flag1, int npeers, int n_own, int cap, int nv, int epoch) {
+  __shared__ int s_cnt[2];
+  if (threadIdx.x < 2) {
+    int c = 0;
+    if (threadIdx.x < npeers) {
+      const int *flag = threadIdx.x == 0 ? flag0 : flag1;
+      if (!wait_epoch(flag, epoch)) sd->error = 3;
+      else c = min(reinterpret_cast<const volatile int *>(flag)[1], cap);
+    }
+    s_cnt[threadIdx.x] = c;
+  }
+  __syncthreads();
+  const int p = blockIdx.x / cap, s = blockIdx.x % cap;
+  const int cnt0 = s_cnt[0], cnt1 = s_cnt[1];
+  if (blockIdx.x == 0 && threadIdx.x == 0) { sd->n_ghost = cnt0 + cnt1; sd->n_total = n_own + cnt0 + cnt1; }
+  const int cnt = p == 0 ? cnt0 : cnt1;
+  if (s >= cnt) return;
+  const unsigned char *buf = p == 0 ? buf0 : buf1;
+  const int c = n_own + (p == 0 ? 0 : cnt0) + s;
+  if (threadIdx.x == 0) gid[c] = __ldcg(reinterpret_cast<const int *>(buf + msg_off_gid()) + s);
+  if (threadIdx.x < BND) bnd[BND * (size_t)c + threadIdx.x] = __ldcg(reinterpret_cast<const float4 *>(buf + msg_off_bnd(cap)) + BND * s + threadIdx.x);
+  const float4 *src = reinterpret_cast<const float4 *>(buf + msg_off_pos(cap)) + (size_t)s * nv;
+  float4 *dst = pos + (size_t)c * nv;
+  for (int v = threadIdx.x; v < nv; v += blockDim.x) dst[v] = __ldcg(src + v);
+}
+
 __global__ void iota_kernel(int *a, int n, int base) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = base + i;
@@ -233,47 +360,76 @@ int shard_exchange(dpm3d_ctx *h, int pbc, float L) {
   Nccl &N = nccl();
   ncclComm_t comm = static_cast<ncclComm_t>(h->comm);
   float4 *pos = h->pos[h->cur], *bnd = h->bnd[h->cur];
-  // DPM_TRACE: device time of each phase of ONE exchange (the 400th of the process), events on the stream
+  // DPM_TRACE: device time of each phase of ONE exchange (the 150th of the process), events on the stream
   static const bool trace = getenv("DPM_TRACE") != nullptr;
   static int ncall = 0;
-  const bool tr = trace && ++ncall == 400;
+  const bool tr = trace && ++ncall == 150;
   cudaEvent_t tev[7] = {};
   auto mark = [&](int i) { if (tr) { cudaEventCreate(&tev[i]); cudaEventRecord(tev[i], h->stream); } };
   mark(0);
   shard_prepare_kernel<<<PREP_CTAS, 256, 0, h->stream>>>(bnd, h->nc, h->st, h->gather_send,
                                                          h->att_active ? ATT_REACH / RANGE_HEADROOM * 1.0001f : 0.0f, h->prep_partial, h->prep_ticket);
   mark(1);
-  DPM_NCCL_TRY(N.AllGather(h->gather_send, h->gather_all, GATHER, ncclFloat, comm, h->stream));
+  const int epoch = ++h->halo_epoch, par = epoch & 1;
+  const InboxLayout IL = inbox_layout(h->msg_bytes, h->nranks);
+  if (h->halo_p2p) {
+    PeerPtrs pp;
+    for (int r = 0; r < h->nranks; r++) pp.inbox[r] = h->peer_inbox[r];
+    shard_mailbox_kernel<<<1, (h->nranks + 31) / 32 * 32, 0, h->stream>>>(h->gather_send, h->gather_all, pp, h->inbox, IL, h->rank, h->nranks, epoch, h->sd);
+  } else {
+    DPM_NCCL_TRY(N.AllGather(h->gather_send, h->gather_all, GATHER, ncclFloat, comm, h->stream));
+  }
   mark(2);
   shard_select_kernel<<<1, 256, 0, h->stream>>>(bnd, h->nc, h->st, h->sd, h->gather_all, h->rank, h->nranks, h->npeers, h->peer[0],
                                                  h->npeers > 1 ? h->peer[1] : -1, h->sendlist[0], h->sendlist[1], h->ghost_cap,
                                                  h->skin_rel, pbc, L);
   mark(3);
-  shard_pack_kernel<<<h->ghost_cap * h->npeers, 128, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->sendlist[0], h->sendlist[1],
-                                                                      h->sendbuf[0], h->sendbuf[1], h->ghost_cap, h->nv);
-  DPM_CUDA_TRY(cudaGetLastError());
-  mark(4);
-  DPM_NCCL_TRY(N.GroupStart());
-  for (int p = 0; p < h->npeers; p++) {
-    DPM_NCCL_TRY(N.Send(h->sendbuf[p], h->msg_bytes, ncclChar, h->peer[p], comm, h->stream));
-    DPM_NCCL_TRY(N.Recv(h->recvbuf[p], h->msg_bytes, ncclChar, h->peer[p], comm, h->stream));
+  if (h->halo_p2p) {
+    // my peer p sees me on its other side (with two ranks the single peer is both neighbours: side 0)
+    unsigned char *dst[2] = {nullptr, nullptr};
+    int *dflag[2] = {nullptr, nullptr};
+    for (int p = 0; p < h->npeers; p++) {
+      const int side = h->npeers == 1 ? 0 : 1 - p;
+      dst[p] = h->peer_inbox[h->peer[p]] + IL.msg(par, side);
+      dflag[p] = reinterpret_cast<int *>(h->peer_inbox[h->peer[p]] + IL.off_flag) + 2 * (par * 2 + side);
+    }
+    shard_push_kernel<<<h->ghost_cap * h->npeers, 128, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->sendlist[0], h->sendlist[1], dst[0], dst[1],
+                                                                        dflag[0], dflag[1], h->ghost_cap, h->nv, epoch);
+    DPM_CUDA_TRY(cudaGetLastError());
+    mark(4);
+    mark(5);
+    const int *mflag = reinterpret_cast<const int *>(h->inbox + IL.off_flag);
+    shard_unpack_p2p_kernel<<<h->ghost_cap * h->npeers, 128, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->inbox + IL.msg(par, 0), h->inbox + IL.msg(par, 1),
+                                                                              mflag + 2 * (par * 2 + 0), mflag + 2 * (par * 2 + 1), h->npeers, h->nc,
+                                                                              h->ghost_cap, h->nv, epoch);
+    DPM_CUDA_TRY(cudaGetLastError());
+  } else {
+    shard_pack_kernel<<<h->ghost_cap * h->npeers, 128, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->sendlist[0], h->sendlist[1],
+                                                                        h->sendbuf[0], h->sendbuf[1], h->ghost_cap, h->nv);
+    DPM_CUDA_TRY(cudaGetLastError());
+    mark(4);
+    DPM_NCCL_TRY(N.GroupStart());
+    for (int p = 0; p < h->npeers; p++) {
+      DPM_NCCL_TRY(N.Send(h->sendbuf[p], h->msg_bytes, ncclChar, h->peer[p], comm, h->stream));
+      DPM_NCCL_TRY(N.Recv(h->recvbuf[p], h->msg_bytes, ncclChar, h->peer[p], comm, h->stream));
+    }
+    DPM_NCCL_TRY(N.GroupEnd());
+    mark(5);
+    shard_unpack_kernel<<<h->ghost_cap * h->npeers, 128, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->recvbuf[0], h->recvbuf[1], h->npeers,
+                                                                          h->nc, h->ghost_cap, h->nv);
+    DPM_CUDA_TRY(cudaGetLastError());
   }
-  DPM_NCCL_TRY(N.GroupEnd());
-  mark(5);
-  shard_unpack_kernel<<<h->ghost_cap * h->npeers, 128, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->recvbuf[0], h->recvbuf[1], h->npeers,
-                                                                        h->nc, h->ghost_cap, h->nv);
-  DPM_CUDA_TRY(cudaGetLastError());
   mark(6);
   if (tr) {
     cudaEventSynchronize(tev[6]);
     float t[6];
     for (int i = 0; i < 6; i++) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
-    fprintf(stderr, "[dpm3d] rank %d halo exchange (us): prepare %.1f  allgather %.1f  select %.1f  pack %.1f  send/recv %.1f  unpack %.1f  total %.1f\n",
-            h->rank, t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f, t[4] * 1e3f, t[5] * 1e3f, (t[0] + t[1] + t[2] + t[3] + t[4] + t[5]) * 1e3f);
+    fprintf(stderr, "[dpm3d] rank %d halo exchange, %s (us): prepare %.1f  allgather|mailbox %.1f  select %.1f  pack|push %.1f  send/recv %.1f  unpack %.1f  total %.1f\n",
+            h->rank, h->halo_p2p ? "peer-memory path" : "NCCL path", t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f, t[4] * 1e3f, t[5] * 1e3f, (t[0] + t[1] + t[2] + t[3] + t[4] + t[5]) * 1e3f);
     for (auto &e : tev) cudaEventDestroy(e);
   }
-  h->stats.launches += 4;
-  h->stats.halo_bytes += (uint64_t)h->msg_bytes * h->npeers;
+  h->stats.launches += h->halo_p2p ? 5 : 4;
+  if (!h->halo_p2p) h->stats.halo_bytes += (uint64_t)h->msg_bytes * h->npeers;
   return DPM_OK;
 }
 
@@ -281,12 +437,24 @@ int shard_check(dpm3d_ctx *h) {
   ShardDev sd;
   DPM_CUDA_TRY(cudaMemcpyAsync(&sd, h->sd, sizeof(ShardDev), cudaMemcpyDeviceToHost, h->stream));
   DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->halo_p2p) h->stats.halo_bytes = sd.sent_bytes;  // actual bytes stored into the peers' inboxes since the last upload
+  if (sd.error == 3) return fail(DPM_ERR_NCCL, "halo exchange: a neighbouring rank did not answer within the time limit");
   if (sd.error == 1) return fail(DPM_ERR_RUNTIME, "halo overflow: more boundary cells than max_ghost per neighbouring slab");
   if (sd.error == 2) return fail(DPM_ERR_RUNTIME, "slab decomposition too thin: a cell interacts beyond the adjacent slabs");
   return DPM_OK;
 }
 
+void shard_reset_counters(dpm3d_ctx *h) {
+  if (h->sd) cudaMemsetAsync(&h->sd->sent_bytes, 0, sizeof(unsigned long long), h->stream);
+}
+
 void shard_free(dpm3d_ctx *h) {
+  if (h->inbox) {
+    for (int r = 0; r < h->nranks; r++)
+      if (r != h->rank && h->peer_inbox[r]) cudaIpcCloseMemHandle(h->peer_inbox[r]);
+    cudaFree(h->inbox);
+    h->inbox = nullptr;
+  }
   void *ptrs[] = {h->prep_partial, h->prep_ticket, h->gid, h->sd, h->gather_send, h->gather_all, h->sendbuf[0], h->sendbuf[1], h->recvbuf[0], h->recvbuf[1],
                   h->sendlist[0], h->sendlist[1]};
   for (void *p : ptrs) if (p) cudaFree(p);
@@ -367,6 +535,58 @@ int dpm3d_shard_init(dpm3d_t *h, int rank, int nranks, const uint8_t id[128], in
   ncclComm_t comm = nullptr;
   DPM_NCCL_TRY(nccl().CommInitRank(&comm, nranks, u, rank));
   h->comm = comm;
+  // ---- peer-memory path: one inbox per rank, mapped by every other rank through CUDA IPC (handles all-gathered once) ----
+  h->halo_p2p = false;
+  if (!getenv("DPM_HALO_NCCL")) {
+    const InboxLayout IL = inbox_layout(h->msg_bytes, nranks);
+    h->inbox_bytes = IL.total;
+    DPM_CUDA_TRY(cudaMalloc(&h->inbox, IL.total));
+    DPM_CUDA_TRY(cudaMemset(h->inbox, 0, IL.total));
+    cudaIpcMemHandle_t mine;
+    bool ok = cudaIpcGetMemHandle(&mine, h->inbox) == cudaSuccess;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    unsigned char *d_send = nullptr, *d_all = nullptr;
+    DPM_CUDA_TRY(cudaMalloc(&d_send, 64 + 64));
+    DPM_CUDA_TRY(cudaMalloc(&d_all, (size_t)128 * nranks));
+    unsigned char blob[128];
+    memset(blob, 0, sizeof blob);
+    memcpy(blob, &mine, 64);
+    blob[64] = ok ? 1 : 0;
+    DPM_CUDA_TRY(cudaMemcpy(d_send, blob, 128, cudaMemcpyHostToDevice));
+    DPM_NCCL_TRY(nccl().AllGather(d_send, d_all, 128, ncclChar, comm, h->stream));
+    std::vector<unsigned char> all((size_t)128 * nranks);
+    DPM_CUDA_TRY(cudaMemcpyAsync(all.data(), d_all, all.size(), cudaMemcpyDeviceToHost, h->stream));
+    DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(d_send); cudaFree(d_all);
+    bool all_ok = true;
+    for (int r = 0; r < nranks; r++) all_ok = all_ok && all[(size_t)128 * r + 64] == 1;
+    if (all_ok) {
+      for (int r = 0; r < nranks && all_ok; r++) {
+        if (r == rank) { h->peer_inbox[r] = h->inbox; continue; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, &all[(size_t)128 * r], 64);
+        void *ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { all_ok = false; cudaGetLastError(); break; }
+        h->peer_inbox[r] = static_cast<unsigned char *>(ptr);
+      }
+    }
+    // every rank must take the same path: agree through one more all-gather of the outcome
+    {
+      unsigned char *d_f = nullptr, *d_fa = nullptr;
+      DPM_CUDA_TRY(cudaMalloc(&d_f, 16));
+      DPM_CUDA_TRY(cudaMalloc(&d_fa, (size_t)16 * nranks));
+      unsigned char f16[16] = {(unsigned char)(all_ok ? 1 : 0)};
+      DPM_CUDA_TRY(cudaMemcpy(d_f, f16, 16, cudaMemcpyHostToDevice));
+      DPM_NCCL_TRY(nccl().AllGather(d_f, d_fa, 16, ncclChar, comm, h->stream));
+      std::vector<unsigned char> fa((size_t)16 * nranks);
+      DPM_CUDA_TRY(cudaMemcpyAsync(fa.data(), d_fa, fa.size(), cudaMemcpyDeviceToHost, h->stream));
+      DPM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+      cudaFree(d_f); cudaFree(d_fa);
+      for (int r = 0; r < nranks; r++) all_ok = all_ok && fa[(size_t)16 * r] == 1;
+    }
+    h->halo_p2p = all_ok;
+    if (!all_ok && getenv("DPM_TRACE")) fprintf(stderr, "[dpm3d] rank %d: peer-memory halo path unavailable (CUDA IPC), using the NCCL path\n", rank);
+  }
   return DPM_OK;
 }
 
