@@ -69,7 +69,13 @@ __device__ __forceinline__ bool edge_toggles(float2 p, float2 vi, float2 vj, boo
     }
   }
   if ((diy > 0.0f) == (djy > 0.0f)) return false;
-  const float xc = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(djx, dix), __fsub_rn(0.0f, diy)), __fsub_rn(djy, diy)), dix);
+  // 0 < (djx - dix) * (0 - diy) / (djy - diy) + dix   (:191-194).  The IEEE division (a ~15-instruction subroutine) only
+  // decides the sign when the sum nearly cancels: a reciprocal-based quotient within 4 ulp settles every other case.
+  const float num = __fmul_rn(__fsub_rn(djx, dix), __fsub_rn(0.0f, diy)), den = __fsub_rn(djy, diy);
+  const float qa = num * __frcp_rn(den);
+  const float sa = qa + dix;
+  if (fabsf(sa) > 1e-5f * (fabsf(qa) + fabsf(dix))) return 0.0f < sa;
+  const float xc = __fadd_rn(__fdiv_rn(num, den), dix);
   return 0.0f < xc;
 }
 
@@ -162,12 +168,51 @@ __global__ void __launch_bounds__(T2D, 7) dpm2d_step_kernel(Step2DParams P) {
   const bool own_cull_ok = !P.pbc || ((hxi + l0 < 0.25f * P.L) && (hyi + l0 < 0.25f * P.L));
   unsigned evals = 0;
   if (doAtt || doRep) {
-    for (int k = 0; k < ncand; k++) {
-      const int cj = P.cand[(size_t)ci * P.K + k];
-      const float4 bj0 = P.bnd_in[3 * (size_t)cj], bj1 = P.bnd_in[3 * (size_t)cj + 1];
+    // Candidates are taken 32 at a time: every lane loads ONE candidate's id, bounding box and vertex count (one round of
+    // global-memory latency for the whole batch instead of two dependent loads per candidate on the warp's critical path)
+    // and decides, exactly, whether ANY vertex of this cell can pass the per-vertex culls for it; the survivors are then
+    // visited in ascending order (the reference's summation order) with their data broadcast out of the owning lane.
+    for (int cbase = 0; cbase < ncand; cbase += 32) {
+     const int kk = cbase + lane;
+     int my_cj = -1, my_nj = 0;
+     float4 mb0 = make_float4(0.f, 0.f, 0.f, 0.f), mb1 = mb0;
+     bool pass = false;
+     if (kk < ncand) {
+       my_cj = P.cand[(size_t)ci * P.K + kk];
+       mb0 = P.bnd_in[3 * (size_t)my_cj]; mb1 = P.bnd_in[3 * (size_t)my_cj + 1];
+       my_nj = P.nv[my_cj];
+       const float hx = 0.5f * (mb1.x - mb0.x), hy = 0.5f * (mb1.y - mb0.y);
+       const float cxj = 0.5f * (mb0.x + mb1.x), cyj = 0.5f * (mb0.y + mb1.y);
+       const bool att_cull_ok = !P.pbc || ((hx + l0 < 0.25f * P.L) && (hy + l0 < 0.25f * P.L));
+       bool repPossible = false, attPossible = false;
+       if (doRep) {
+         const bool ovx = !(bi1.x < mb0.x || bi0.x > mb1.x), ovy = !(bi1.y < mb0.y || bi0.y > mb1.y);
+         const float mx = fmaxf(fmaxf(fabsf(bi0.x - mb0.x), fabsf(bi1.x - mb0.x)), fmaxf(fabsf(bi0.x - mb1.x), fabsf(bi1.x - mb1.x)));
+         const float my = fmaxf(fmaxf(fabsf(bi0.y - mb0.y), fabsf(bi1.y - mb0.y)), fmaxf(fabsf(bi0.y - mb1.y), fabsf(bi1.y - mb1.y)));
+         repPossible = (ovx || (P.pbc && mx > P.L)) && (ovy || (P.pbc && my > P.L));
+       }
+       if (doAtt) {
+         float dx = cxi - cxj, dy = cyi - cyj;
+         if (P.pbc) { dx -= P.L * roundf(dx * invL); dy -= P.L * roundf(dy * invL); }
+         const float ax = fmaxf(fabsf(dx) - hx - hxi, 0.0f), ay = fmaxf(fabsf(dy) - hy - hyi, 0.0f);
+         attPossible = !att_cull_ok || !own_cull_ok || (ax * ax + ay * ay <= l0 * l0 * 1.001f + 1e-12f);
+       }
+       pass = repPossible || attPossible;
+     }
+     unsigned mcand = __ballot_sync(0xffffffffu, pass);
+     while (mcand) {
+      const int csrc = __ffs(mcand) - 1;
+      mcand &= mcand - 1;
+      const int cj = __shfl_sync(0xffffffffu, my_cj, csrc);
+      const int nj_known = __shfl_sync(0xffffffffu, my_nj, csrc);
+      float4 bj0, bj1;
+      bj0.x = __shfl_sync(0xffffffffu, mb0.x, csrc); bj0.y = __shfl_sync(0xffffffffu, mb0.y, csrc);
+      bj1.x = __shfl_sync(0xffffffffu, mb1.x, csrc); bj1.y = __shfl_sync(0xffffffffu, mb1.y, csrc);
       const float hx = 0.5f * (bj1.x - bj0.x), hy = 0.5f * (bj1.y - bj0.y);
       const float cxj = 0.5f * (bj0.x + bj1.x), cyj = 0.5f * (bj0.y + bj1.y);
       const bool att_cull_ok = !P.pbc || ((hx + l0 < 0.25f * P.L) && (hy + l0 < 0.25f * P.L));
+      // rij -= L * round(rij / L) (:254-256) is a no-op for every vertex pair of the two cells unless they can be half a box apart
+      const bool wrapPossible = P.pbc && (fmaxf(fabsf(bi0.x - bj1.x), fabsf(bi1.x - bj0.x)) > halfL || fmaxf(fabsf(bi0.y - bj1.y), fabsf(bi1.y - bj0.y)) > halfL);
       int nj = 0, nnear = 0;
       bool staged = false, nearBuilt = false;
       for (int ch = 0; ch < nchunk; ch++) {
@@ -195,7 +240,7 @@ __global__ void __launch_bounds__(T2D, 7) dpm2d_step_kernel(Step2DParams P) {
         const unsigned mFar = __ballot_sync(0xffffffffu, far);
         if ((mAtt | mRep) == 0) continue;
         if (!staged) {  // stage the neighbour's ring once per candidate
-          nj = P.nv[cj];
+          nj = nj_known;
           const float2 *gN = P.pos_in + (size_t)cj * S;
           __syncwarp();
           for (int v = lane; v < nj; v += 32) sN[v] = gN[v];
@@ -235,10 +280,11 @@ __global__ void __launch_bounds__(T2D, 7) dpm2d_step_kernel(Step2DParams P) {
             // narrow band where the two could disagree.
             const float c = P.Kat / (float)n / l0;
             const float l0sq = l0 * l0, l0sq_lo = l0sq * 0.99999f, l0sq_hi = l0sq * 1.00001f;
+#pragma unroll 4
             for (int t = 0; t < nnear; t++) {
               const float2 q = sNear[t];
               float rx = q.x - p.x, ry = q.y - p.y;
-              if (P.pbc) {  // rij -= L * round(rij / L)  (:254-256); a no-op unless |r| > L/2
+              if (wrapPossible) {  // rij -= L * round(rij / L)  (:254-256); a no-op unless |r| > L/2
                 if (fabsf(rx) > halfL) rx -= P.L * roundf(rx / P.L);
                 if (fabsf(ry) > halfL) ry -= P.L * roundf(ry / P.L);
               }
@@ -272,6 +318,7 @@ __global__ void __launch_bounds__(T2D, 7) dpm2d_step_kernel(Step2DParams P) {
         }
         __syncwarp();
       }
+     }
     }
   }
   __syncwarp();

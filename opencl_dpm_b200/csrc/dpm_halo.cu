@@ -165,12 +165,21 @@ __global__ void __launch_bounds__(256) shard_prepare_kernel(const float4 *bnd, i
     last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (!last || threadIdx.x != 0) return;
+  if (!last) return;
+  // the last CTA folds the partials in parallel (a single thread walking them took 12 of this kernel's 19 us)
   __threadfence();
   rlo = INFINITY; rhi = -INFINITY; ext = 0.f; pad = 0.f;
-  for (int b = 0; b < (int)gridDim.x; b++) {
-    const volatile float *p = partial + 4 * b;
-    rlo = fminf(rlo, p[0]); rhi = fmaxf(rhi, p[1]); ext = fmaxf(ext, p[2]); pad = fmaxf(pad, p[3]);
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+    const float4 q = __ldcg(reinterpret_cast<const float4 *>(partial) + b);
+    rlo = fminf(rlo, q.x); rhi = fmaxf(rhi, q.y); ext = fmaxf(ext, q.z); pad = fmaxf(pad, q.w);
+  }
+  rlo = warp_min(rlo); rhi = warp_max(rhi); ext = warp_max(ext); pad = warp_max(pad);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { s[w][0] = rlo; s[w][1] = rhi; s[w][2] = ext; s[w][3] = pad; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int i = 0; i < (int)blockDim.x / 32; i++) {
+    rlo = fminf(rlo, s[i][0]); rhi = fmaxf(rhi, s[i][1]); ext = fmaxf(ext, s[i][2]); pad = fmaxf(pad, s[i][3]);
   }
   *ticket = 0u;
   out[0] = st->rebuild ? 1.f : 0.f;
@@ -306,10 +315,11 @@ __global__ void shard_push_kernel(const float4 *pos, const float4 *bnd, const in
     const float4 *src = pos + (size_t)c * nv;
     for (int v = threadIdx.x; v < nv; v += blockDim.x) dst[v] = src[v];
   }
-  // the last CTA of this peer to finish releases the arrival flag (count first, epoch last)
-  __threadfence_system();
+  // the last CTA of this peer to finish releases the arrival flag (count first, epoch last).  One system-scope fence per CTA,
+  // by thread 0 behind the CTA barrier (cumulative over the other threads' stores), and none for CTAs that stored nothing.
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (s < cnt) __threadfence_system();
     const unsigned done = atomicAdd(&sd->push_ticket[p], 1u);
     if (done == (unsigned)cap - 1u) {
       sd->push_ticket[p] = 0u;
@@ -393,7 +403,7 @@ int shard_exchange(dpm3d_ctx *h, int pbc, float L) {
       dst[p] = h->peer_inbox[h->peer[p]] + IL.msg(par, side);
       dflag[p] = reinterpret_cast<int *>(h->peer_inbox[h->peer[p]] + IL.off_flag) + 2 * (par * 2 + side);
     }
-    shard_push_kernel<<<h->ghost_cap * h->npeers, 128, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->sendlist[0], h->sendlist[1], dst[0], dst[1],
+    shard_push_kernel<<<h->ghost_cap * h->npeers, 256, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->sendlist[0], h->sendlist[1], dst[0], dst[1],
                                                                         dflag[0], dflag[1], h->ghost_cap, h->nv, epoch);
     DPM_CUDA_TRY(cudaGetLastError());
     mark(4);
