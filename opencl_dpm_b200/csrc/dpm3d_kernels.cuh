@@ -576,8 +576,10 @@ __device__ __forceinline__ void patch_boxes(const Step3DParams &P, int ci, int t
 // candidate neighbour (cell list) whose box overlaps the cell's own; survivors are written, ordered by (thread,
 // vertex, ascending neighbour), into a contiguous range of the global unit list reserved with one atomicAdd.
 // ---------------------------------------------------------------------------------
-constexpr int UNITS_THREADS = 256;
-constexpr int UNITS_VPT = 4;  // nv <= 1024
+#ifndef DPM_UNITS_THREADS
+#define DPM_UNITS_THREADS 128
+#endif
+constexpr int UNITS_THREADS = DPM_UNITS_THREADS;
 constexpr int UNITS_KMAX = 128;
 
 // ATT: DPM3D_ATTRACT is selected (the default instantiation carries none of the attraction code)
@@ -648,41 +650,40 @@ __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams
     if (tid == 0) { P.unit_base[ci] = 0; P.unit_cnt[ci] = 0; P.vlist_cnt[ci] = 0; }
     return;
   }
-  float4 myp[UNITS_VPT];
-#pragma unroll
-  for (int j = 0; j < UNITS_VPT; j++) {
-    const int v = tid + j * UNITS_THREADS;
-    myp[j] = (v < nv) ? P.pos_in[(size_t)ci * nv + v] : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  // One pass of tests: with at most 32 candidates (the default capacity) the survivors of a vertex are kept as a bit mask
-  // and the emit pass below only walks the set bits; longer lists repeat the tests when emitting.
-  const bool masked = ncand <= 32;
-  int cntj[UNITS_VPT];
-  unsigned hitm[UNITS_VPT];
-  int cnt = 0;
-#pragma unroll
-  for (int j = 0; j < UNITS_VPT; j++) {
-    const int v = tid + j * UNITS_THREADS;
-    cntj[j] = 0;
-    hitm[j] = 0u;
-    if (v < nv) {
-      const float4 p = myp[j];
-      for (int k = 0; k < ncand; k++) {
-        if (sCand[k] < 0) continue;
-        const float4 lo = sLo[k], hi = sHi[k], sp = sSph[k];
-        const float dx = p.x - sp.x, dy = p.y - sp.y, dz = p.z - sp.z;
-        const bool in = !(p.x < lo.x || p.x > hi.x || p.y < lo.y || p.y > hi.y || p.z < lo.z || p.z > hi.z) &&
-                        (dx * dx + dy * dy + dz * dz) <= sp.w;
-        cntj[j] += in ? 1 : 0;
-        hitm[j] |= (in ? 1u : 0u) << (k & 31);
-      }
-      cnt += cntj[j];
+  // The active candidates, compacted (ascending k = ascending neighbour id).
+  __shared__ int sAct[UNITS_KMAX];
+  __shared__ int sNact;
+  if (warp == 0) {
+    int nb = 0;
+    for (int k0 = 0; k0 < ncand; k0 += 32) {
+      const int k = k0 + lane;
+      const bool a = k < ncand && sCand[k] >= 0;
+      const unsigned b = __ballot_sync(0xffffffffu, a);
+      if (a) sAct[nb + __popc(b & ((1u << lane) - 1u))] = k;
+      nb += __popc(b);
     }
+    if (lane == 0) sNact = nb;
+  }
+  __syncthreads();
+  const int na = sNact;
+  const float4 *gP = P.pos_in + (size_t)ci * nv;
+  auto inside = [&](const float4 &p, int k) {
+    const float4 lo = sLo[k], hi = sHi[k], sp = sSph[k];
+    const float dx = p.x - sp.x, dy = p.y - sp.y, dz = p.z - sp.z;
+    return !(p.x < lo.x || p.x > hi.x || p.y < lo.y || p.y > hi.y || p.z < lo.z || p.z > hi.z) && (dx * dx + dy * dy + dz * dz) <= sp.w;
+  };
+  // Two passes over the thread's vertices (count, then emit) instead of per-vertex state in registers: the kernel is bound by
+  // the latency of its dependent global loads times the number of CTA waves, so small CTAs with few registers — many of them
+  // resident — matter more than the repeated tests (the second pass reads the vertices out of L1 / L2).
+  int cnt = 0, nvh = 0;
+  for (int v = tid; v < nv; v += UNITS_THREADS) {
+    const float4 p = gP[v];
+    int c = 0;
+    for (int a = 0; a < na; a++) c += inside(p, sAct[a]) ? 1 : 0;
+    cnt += c;
+    nvh += c > 0 ? 1 : 0;
   }
   // exclusive scans of the per-thread counts: units, and vertices that have any
-  int nvh = 0;
-#pragma unroll
-  for (int j = 0; j < UNITS_VPT; j++) nvh += cntj[j] > 0 ? 1 : 0;
   int incl = cnt, vincl = nvh;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -711,34 +712,23 @@ __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams
     P.vlist_cnt[ci] = base < 0 ? 0 : vtotal;
   }
   __syncthreads();
-  {  // the cell's vertices that have units, with (offset, count) into its unit range: all the step kernel has to visit
-    int off = woff + incl - cnt;
-    uint2 *vl = P.vlist + (size_t)ci * nv + (vwoff + vincl - nvh);
-#pragma unroll
-    for (int j = 0; j < UNITS_VPT; j++) {
-      const int v = tid + j * UNITS_THREADS;
-      if (v < nv && cntj[j] > 0) *vl++ = make_uint2((unsigned)v, ((unsigned)off << 8) | (unsigned)min(cntj[j], 255));
-      off += cntj[j];
+  if (total == 0 || sBase < 0 || cnt == 0) return;
+  // emit: the thread's units in (vertex, ascending neighbour) order, and for every vertex that has any the entry
+  // (vertex, offset within the cell's unit range << 8 | count) of the list the step kernel visits
+  int off = woff + incl - cnt;
+  uint2 *vl = P.vlist + (size_t)ci * nv + (vwoff + vincl - nvh);
+  int2 *out = P.unit_rec + sBase + off;
+  for (int v = tid; v < nv; v += UNITS_THREADS) {
+    const float4 p = gP[v];
+    int c = 0;
+    for (int a = 0; a < na; a++) {
+      const int k = sAct[a];
+      if (inside(p, k)) { out[c] = make_int2(ci * nv + v, sCand[k]); c++; }
     }
-  }
-  if (total == 0 || sBase < 0) return;
-  int2 *out = P.unit_rec + sBase + woff + incl - cnt;
-#pragma unroll
-  for (int j = 0; j < UNITS_VPT; j++) {
-    const int v = tid + j * UNITS_THREADS;
-    if (v < nv && masked) {
-      for (unsigned m = hitm[j]; m; m &= m - 1) *out++ = make_int2(ci * nv + v, sCand[__ffs(m) - 1]);  // ascending k = ascending cj
-    } else if (v < nv) {
-      const float4 p = myp[j];
-      for (int k = 0; k < ncand; k++) {
-        const int cj = sCand[k];
-        if (cj < 0) continue;
-        const float4 lo = sLo[k], hi = sHi[k], sp = sSph[k];
-        const float dx = p.x - sp.x, dy = p.y - sp.y, dz = p.z - sp.z;
-        if (!(p.x < lo.x || p.x > hi.x || p.y < lo.y || p.y > hi.y || p.z < lo.z || p.z > hi.z) &&
-            (dx * dx + dy * dy + dz * dz) <= sp.w)
-          *out++ = make_int2(ci * nv + v, cj);
-      }
+    if (c > 0) {
+      *vl++ = make_uint2((unsigned)v, ((unsigned)off << 8) | (unsigned)min(c, 255));
+      out += c;
+      off += c;
     }
   }
 }
