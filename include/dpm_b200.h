@@ -92,6 +92,12 @@ const char *dpm_version(void);
 /* Copies the calling thread's last error message (NUL-terminated) into buf. */
 int dpm_last_error(char *buf, size_t n);
 int dpm_device_count(int *count);
+/* Page-lock (and later release) a caller-owned host buffer so that the uploads / downloads of dpm*_upload, dpm*_download
+ * and dpm*_euler_update run at full PCIe speed without a bounce buffer.  Optional: every entry point also accepts pageable
+ * memory (the reference's host arrays are plain std::vector storage, src/Tissue3D.cpp:139-141).  Re-pinning a buffer that is
+ * already pinned is not an error. */
+int dpm_pin_host_buffer(void *ptr, size_t bytes);
+int dpm_unpin_host_buffer(void *ptr);
 
 /* Geometry helpers restating the reference constructors (src/cell.cpp:62-158, :12-33) so
  * that flat tissues can be built without the C++ classes. subdiv = 2 is the reference mesh

@@ -26,6 +26,21 @@ int dpm_last_error(char *buf, size_t n) {
   return DPM_OK;
 }
 
+int dpm_pin_host_buffer(void *ptr, size_t bytes) {
+  if (!ptr || !bytes) return dpm::fail(DPM_ERR_INVALID_ARGUMENT, "NULL buffer");
+  const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return DPM_OK; }
+  if (e != cudaSuccess) { cudaGetLastError(); return dpm::fail(DPM_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+  return DPM_OK;
+}
+
+int dpm_unpin_host_buffer(void *ptr) {
+  if (!ptr) return DPM_OK;
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) cudaGetLastError();  // not registered (any more): nothing to release
+  return DPM_OK;
+}
+
 int dpm_device_count(int *count) {
   if (!count) return dpm::fail(DPM_ERR_INVALID_ARGUMENT, "count is NULL");
   *count = 0;

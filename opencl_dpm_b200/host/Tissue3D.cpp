@@ -30,8 +30,23 @@ struct DeviceHandle3D {
   int ncells = 0;
   std::vector<uint32_t> faces;
   bool resident = false;  // the device holds the tissue's current state (StepResident)
-  Packed3D staging;       // host staging of the resident path
+  Packed3D staging;       // host staging, kept between calls (no 84 MB allocation + first touch per call at BASELINE sizes)
+  const float *pinned_v = nullptr, *pinned_f = nullptr;  // page-locked state of the two large staging arrays
+  // (re-)page-lock the large staging arrays after pack3d may have reallocated them; small tissues are not worth the system call
+  void pin() {
+    if (staging.verts.size() < (1u << 18)) return;
+    if (staging.verts.data() != pinned_v) {
+      if (pinned_v) dpm_unpin_host_buffer(const_cast<float *>(pinned_v));
+      pinned_v = dpm_pin_host_buffer(staging.verts.data(), staging.verts.size() * sizeof(float)) == DPM_OK ? staging.verts.data() : nullptr;
+    }
+    if (staging.forces.data() != pinned_f) {
+      if (pinned_f) dpm_unpin_host_buffer(const_cast<float *>(pinned_f));
+      pinned_f = dpm_pin_host_buffer(staging.forces.data(), staging.forces.size() * sizeof(float)) == DPM_OK ? staging.forces.data() : nullptr;
+    }
+  }
   ~DeviceHandle3D() {
+    if (pinned_v) dpm_unpin_host_buffer(const_cast<float *>(pinned_v));
+    if (pinned_f) dpm_unpin_host_buffer(const_cast<float *>(pinned_f));
     if (h) dpm3d_destroy(h);
   }
 };
@@ -128,8 +143,12 @@ static void pack3d(const std::vector<Cell3D> &Cells, int NCELLS, Packed3D &P) {
     }
     faces[3 * fi] = f[0]; faces[3 * fi + 1] = f[1]; faces[3 * fi + 2] = f[2];
   }
-  verts.assign((size_t)NCELLS * NV * 4, 0.0f);
-  forces.assign((size_t)NCELLS * NV * 4, 0.0f);
+  // the staging arrays persist between calls: only (re)sized when the tissue changed — no re-zeroing of 2 x 42 MB per call at
+  // BASELINE sizes; every xyz is written below, the pad lane stays 0 from the first sizing, forces are overwritten by the call
+  if (verts.size() != (size_t)NCELLS * NV * 4) {
+    verts.assign((size_t)NCELLS * NV * 4, 0.0f);
+    forces.assign((size_t)NCELLS * NV * 4, 0.0f);
+  }
   for (auto *x : {&Kv, &Ka, &Ks, &v0, &a0, &l0}) x->assign(NCELLS, 0.0f);
   {  // threaded happy path; anything the checks below would report makes the serial pass run instead
     std::atomic<bool> bad{false};
@@ -238,8 +257,10 @@ static void unpack3d(std::vector<Cell3D> &Cells, int NCELLS, const Packed3D &P) 
 
 void Tissue3D::CLEulerUpdate(int nsteps, float dt) {
   validate_step(nsteps, dt, NCELLS);
-  Packed3D P;
+  if (!dev) dev = std::make_shared<DeviceHandle3D>();
+  Packed3D &P = dev->staging;  // persistent between calls; the arrays are rewritten from Cells by every call
   pack3d(Cells, NCELLS, P);
+  dev->pin();
   const int NF = P.NF, NV = P.NV;
   std::vector<uint32_t> &faces = P.faces;
   std::vector<float> &verts = P.verts, &forces = P.forces, &Kv = P.Kv, &Ka = P.Ka, &Ks = P.Ks, &v0 = P.v0, &a0 = P.a0, &l0 = P.l0;
