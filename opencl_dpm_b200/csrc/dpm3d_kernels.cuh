@@ -739,8 +739,12 @@ __global__ void __launch_bounds__(UNITS_THREADS) dpm3d_units_kernel(Step3DParams
 // ---------------------------------------------------------------------------------
 constexpr int CONTACT_THREADS = 256;
 
+#ifndef DPM_CONTACT_MINB
+#define DPM_CONTACT_MINB 4  // CTAs per SM promised to ptxas for the contact kernel: 64 registers (small spills), 32 instead of 24 warps per SM:
+                            // -13 % in the contact-dominated phases against 80 registers, 48 registers (5 CTAs) is slower again
+#endif
 template <bool ATT>
-__global__ void __launch_bounds__(CONTACT_THREADS) dpm3d_contact_kernel(Step3DParams P) {
+__global__ void __launch_bounds__(CONTACT_THREADS, DPM_CONTACT_MINB) dpm3d_contact_kernel(Step3DParams P) {
   const int lane = threadIdx.x & 31;
   const int g = lane & (UNIT_LANES - 1);
   const int gshift = lane & ~(UNIT_LANES - 1);
