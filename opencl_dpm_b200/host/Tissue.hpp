@@ -40,6 +40,11 @@ public:
   void StepResident(int nsteps, float dt);
   void SyncCells();
   void InvalidateDevice();
+  // extension: zero-copy access to the packed host arrays of the last CLEulerUpdate / SyncCells,
+  // [NCELLS][NV][4] floats; the Python module exposes them as numpy views (PositionsView / ForcesView) instead of the
+  // list-of-lists copies of Cell3D::GetPositions / GetForces (src/CellWrapper.cpp:7-19)
+  std::shared_ptr<std::vector<float>> PackedPositions(int *ncells, int *nv) const;
+  std::shared_ptr<std::vector<float>> PackedForces(int *ncells, int *nv) const;
 
 private:
   std::shared_ptr<DeviceHandle3D> dev;  // created on first use; copies of a Tissue share it

@@ -20,9 +20,20 @@ namespace DPM {
 
 // flat arrays in the C ABI's layout (float4-strided vertices, per-cell scalars), as the reference packs them (:137-197)
 struct Packed3D {
-  int NV = 0, NF = 0;
+  int NV = 0, NF = 0, NC = 0;
   std::vector<uint32_t> faces;
-  std::vector<float> verts, forces, Kv, Ka, Ks, v0, a0, l0;
+  // the two large arrays are shared-owned: zero-copy numpy views (Tissue3D::PackedPositions / PackedForces) keep the array
+  // they look at alive even if a later call re-sizes the staging
+  std::shared_ptr<std::vector<float>> vbuf = std::make_shared<std::vector<float>>(), fbuf = std::make_shared<std::vector<float>>();
+  std::vector<float> &verts() const { return *vbuf; }
+  std::vector<float> &forces() const { return *fbuf; }
+  // a NEW pair of arrays (zeroed) when the tissue's size changed; views of the old pair stay valid
+  void resize(size_t n) {
+    if (vbuf->size() == n) return;
+    vbuf = std::make_shared<std::vector<float>>(n, 0.0f);
+    fbuf = std::make_shared<std::vector<float>>(n, 0.0f);
+  }
+  std::vector<float> Kv, Ka, Ks, v0, a0, l0;
 };
 
 struct DeviceHandle3D {
@@ -34,14 +45,14 @@ struct DeviceHandle3D {
   const float *pinned_v = nullptr, *pinned_f = nullptr;  // page-locked state of the two large staging arrays
   // (re-)page-lock the large staging arrays after pack3d may have reallocated them; small tissues are not worth the system call
   void pin() {
-    if (staging.verts.size() < (1u << 18)) return;
-    if (staging.verts.data() != pinned_v) {
+    if (staging.verts().size() < (1u << 18)) return;
+    if (staging.verts().data() != pinned_v) {
       if (pinned_v) dpm_unpin_host_buffer(const_cast<float *>(pinned_v));
-      pinned_v = dpm_pin_host_buffer(staging.verts.data(), staging.verts.size() * sizeof(float)) == DPM_OK ? staging.verts.data() : nullptr;
+      pinned_v = dpm_pin_host_buffer(staging.verts().data(), staging.verts().size() * sizeof(float)) == DPM_OK ? staging.verts().data() : nullptr;
     }
-    if (staging.forces.data() != pinned_f) {
+    if (staging.forces().data() != pinned_f) {
       if (pinned_f) dpm_unpin_host_buffer(const_cast<float *>(pinned_f));
-      pinned_f = dpm_pin_host_buffer(staging.forces.data(), staging.forces.size() * sizeof(float)) == DPM_OK ? staging.forces.data() : nullptr;
+      pinned_f = dpm_pin_host_buffer(staging.forces().data(), staging.forces().size() * sizeof(float)) == DPM_OK ? staging.forces().data() : nullptr;
     }
   }
   ~DeviceHandle3D() {
@@ -132,7 +143,7 @@ static void pack3d(const std::vector<Cell3D> &Cells, int NCELLS, Packed3D &P) {
   const int NF = P.NF = !Cells.empty() ? (int)Cells[0].nfaces() : (int)Cell3D::NF;
   const int NV = P.NV = !Cells.empty() ? (int)Cells[0].nverts() : (int)Cell3D::NV;
   std::vector<uint32_t> &faces = P.faces;
-  std::vector<float> &verts = P.verts, &forces = P.forces, &Kv = P.Kv, &Ka = P.Ka, &Ks = P.Ks, &v0 = P.v0, &a0 = P.a0, &l0 = P.l0;
+  std::vector<float> &Kv = P.Kv, &Ka = P.Ka, &Ks = P.Ks, &v0 = P.v0, &a0 = P.a0, &l0 = P.l0;
   faces.assign(3 * (size_t)NF, 0);
   for (int fi = 0; fi < NF; fi++) {
     const auto &f = Cells[0].Faces[fi];
@@ -145,10 +156,9 @@ static void pack3d(const std::vector<Cell3D> &Cells, int NCELLS, Packed3D &P) {
   }
   // the staging arrays persist between calls: only (re)sized when the tissue changed — no re-zeroing of 2 x 42 MB per call at
   // BASELINE sizes; every xyz is written below, the pad lane stays 0 from the first sizing, forces are overwritten by the call
-  if (verts.size() != (size_t)NCELLS * NV * 4) {
-    verts.assign((size_t)NCELLS * NV * 4, 0.0f);
-    forces.assign((size_t)NCELLS * NV * 4, 0.0f);
-  }
+  P.resize((size_t)NCELLS * NV * 4);
+  P.NC = NCELLS;
+  std::vector<float> &verts = P.verts();
   for (auto *x : {&Kv, &Ka, &Ks, &v0, &a0, &l0}) x->assign(NCELLS, 0.0f);
   {  // threaded happy path; anything the checks below would report makes the serial pass run instead
     std::atomic<bool> bad{false};
@@ -208,7 +218,7 @@ static void pack3d(const std::vector<Cell3D> &Cells, int NCELLS, Packed3D &P) {
 // flat -> Cells with the reference's post-conditions and checks (:477-521)
 static void unpack3d(std::vector<Cell3D> &Cells, int NCELLS, const Packed3D &P) {
   const int NV = P.NV;
-  const std::vector<float> &verts = P.verts, &forces = P.forces;
+  const std::vector<float> &verts = P.verts(), &forces = P.forces();
   {  // threaded happy path; anything the checks below would report makes the serial pass run instead
     std::atomic<bool> bad{false};
     parallel_cells(NCELLS, (size_t)NV * 3, [&](int c0, int c1) {
@@ -263,7 +273,7 @@ void Tissue3D::CLEulerUpdate(int nsteps, float dt) {
   dev->pin();
   const int NF = P.NF, NV = P.NV;
   std::vector<uint32_t> &faces = P.faces;
-  std::vector<float> &verts = P.verts, &forces = P.forces, &Kv = P.Kv, &Ka = P.Ka, &Ks = P.Ks, &v0 = P.v0, &a0 = P.a0, &l0 = P.l0;
+  std::vector<float> &verts = P.verts(), &forces = P.forces(), &Kv = P.Kv, &Ka = P.Ka, &Ks = P.Ks, &v0 = P.v0, &a0 = P.a0, &l0 = P.l0;
 
   // ---- device: one handle per tissue, re-created only if the size or topology changed
   try {
@@ -316,7 +326,7 @@ void Tissue3D::StepResident(int nsteps, float dt) {
         dev->ncells = NCELLS;
         dev->faces = P.faces;
       }
-      if (dpm3d_upload(dev->h, P.verts.data(), P.Kv.data(), P.Ka.data(), P.Ks.data(), P.v0.data(), P.a0.data(), P.l0.data()) != DPM_OK)
+      if (dpm3d_upload(dev->h, P.verts().data(), P.Kv.data(), P.Ka.data(), P.Ks.data(), P.v0.data(), P.a0.data(), P.l0.data()) != DPM_OK)
         throw std::runtime_error(last_error());
       dev->resident = true;
     }
@@ -334,12 +344,28 @@ void Tissue3D::StepResident(int nsteps, float dt) {
 void Tissue3D::SyncCells() {
   if (!dev || !dev->h || !dev->resident) return;  // nothing newer on the device than Cells
   Packed3D &P = dev->staging;
-  if (dpm3d_download(dev->h, P.verts.data(), P.forces.data()) != DPM_OK) {
+  if (dpm3d_download(dev->h, P.verts().data(), P.forces().data()) != DPM_OK) {
     dev->resident = false;
     std::cerr << "[ERROR] Exception caught: " << last_error() << std::endl;
     throw std::runtime_error(last_error());
   }
   unpack3d(Cells, NCELLS, P);
+}
+
+// ---- zero-copy views of the packed host arrays (extension) ------------------------------------------
+// The arrays of the last CLEulerUpdate / SyncCells: [NCELLS][NV][4] floats (x, y, z, pad), positions and last-step forces.
+// The returned owner keeps the array alive; the next call on the same tissue rewrites it in place (a live view).
+std::shared_ptr<std::vector<float>> Tissue3D::PackedPositions(int *ncells, int *nv) const {
+  if (!dev || dev->staging.vbuf->empty()) return nullptr;
+  if (ncells) *ncells = dev->staging.NC;
+  if (nv) *nv = dev->staging.NV;
+  return dev->staging.vbuf;
+}
+std::shared_ptr<std::vector<float>> Tissue3D::PackedForces(int *ncells, int *nv) const {
+  if (!dev || dev->staging.fbuf->empty()) return nullptr;
+  if (ncells) *ncells = dev->staging.NC;
+  if (nv) *nv = dev->staging.NV;
+  return dev->staging.fbuf;
 }
 
 }  // namespace DPM

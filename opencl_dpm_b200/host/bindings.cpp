@@ -2,6 +2,7 @@
 // (src/DPMWrapper.cpp:11-17, src/CellWrapper.cpp:7-29, src/TissueWrapper.cpp:7-29),
 // bound to the B200 host classes.  Attribute names, read/write-ness and method names
 // are identical; T.Cells stays copy-on-access through the STL casters.
+#include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
@@ -10,6 +11,15 @@
 
 namespace py = pybind11;
 using namespace DPM;
+
+// numpy view [NCELLS][NV][4] of a shared-owned packed array: no copy, the capsule keeps the array alive
+static py::object packed_view(const std::shared_ptr<std::vector<float>> &buf, int nc, int nv) {
+  if (!buf) return py::none();
+  auto *keep = new std::shared_ptr<std::vector<float>>(buf);
+  py::capsule owner(keep, [](void *p) { delete static_cast<std::shared_ptr<std::vector<float>> *>(p); });
+  return py::array_t<float>({(py::ssize_t)nc, (py::ssize_t)nv, (py::ssize_t)4},
+                            {(py::ssize_t)(sizeof(float) * 4 * nv), (py::ssize_t)(sizeof(float) * 4), (py::ssize_t)sizeof(float)}, buf->data(), owner);
+}
 
 PYBIND11_MODULE(clDPM, m) {
   m.doc() = "Deformable Particle Model — B200-native (CUDA sm_100a) drop-in for OpenCL_DPM's clDPM";
@@ -78,5 +88,9 @@ PYBIND11_MODULE(clDPM, m) {
       .def("StepResident", &Tissue3D::StepResident)
       .def("SyncCells", &Tissue3D::SyncCells)
       .def("InvalidateDevice", &Tissue3D::InvalidateDevice)
+      // extension: zero-copy numpy views [NCELLS][NV][4] (x, y, z, pad) of the positions / last-step forces as the last
+      // CLEulerUpdate or SyncCells left them (None before the first call); the next call rewrites them in place
+      .def("PositionsView", [](const Tissue3D &T) { int nc = 0, nv = 0; auto b = T.PackedPositions(&nc, &nv); return packed_view(b, nc, nv); })
+      .def("ForcesView", [](const Tissue3D &T) { int nc = 0, nv = 0; auto b = T.PackedForces(&nc, &nv); return packed_view(b, nc, nv); })
       .def("Disperse2D", &Tissue3D::Disperse2D);
 }

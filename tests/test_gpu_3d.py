@@ -357,6 +357,38 @@ def test_step_resident_equals_repeated_cleulerupdate():
         B.StepResident(0, 0.01)
 
 
+def test_zero_copy_views_of_positions_and_forces():
+    """Extension: Tissue3D.PositionsView() / ForcesView() are numpy views [NCELLS][NV][4] of the packed host
+    arrays of the last CLEulerUpdate / SyncCells — no copy (the next call rewrites the same memory), equal to what the
+    reference surface returns as lists (Cell3D.Verts / GetForces, src/CellWrapper.cpp:7-19)."""
+    m = H.cldpm()
+    c = m.Cell3D([0.0, 0.0, 0.0], 1.0, 1.0)
+    c.Ka, c.Kv, c.Ks = 2.0, 5.0, 3.0
+    T = m.Tissue3D([c] * 16, 0.35)
+    T.Kre = 25.0
+    H.reset_drand48()
+    T.Disperse2D()
+    assert T.PositionsView() is None  # nothing packed yet
+    T.CLEulerUpdate(5, 0.01)
+    P, F = T.PositionsView(), T.ForcesView()
+    assert P.shape == (16, 162, 4) and F.shape == (16, 162, 4) and P.dtype == np.float32 and not P.flags.owndata
+    cells = T.Cells
+    V = np.stack([np.asarray(x.Verts, np.float32) for x in cells])
+    Fc = np.stack([np.asarray(x.GetForces(), np.float32).T for x in cells])
+    assert np.array_equal(P[:, :, :3], V) and np.array_equal(F[:, :, :3], Fc) and np.abs(Fc).max() > 0
+    addr = P.__array_interface__["data"][0]
+    before = P[:, :, :3].copy()
+    T.CLEulerUpdate(5, 0.01)
+    P2 = T.PositionsView()
+    assert P2.__array_interface__["data"][0] == addr, "the view is the staging array itself, not a copy"
+    assert not np.array_equal(P[:, :, :3], before), "the earlier view shows the new state: same memory"
+    T.StepResident(3, 0.01)
+    T.SyncCells()
+    assert np.array_equal(T.PositionsView()[:, :, :3], np.stack([np.asarray(x.Verts, np.float32) for x in T.Cells]))
+    del T
+    assert np.isfinite(P).all()  # the view keeps the array alive
+
+
 def test_threaded_pack_unpack_equals_flat_path():
     """A tissue large enough for the host classes' threaded pack/unpack (> 2e5 vertices): Tissue3D.CLEulerUpdate must
     equal the C ABI driven with the same flat arrays, bit for bit (positions, last-step forces, Volume)."""
