@@ -79,6 +79,18 @@ __device__ __forceinline__ bool edge_toggles(float2 p, float2 vi, float2 vj, boo
   return 0.0f < xc;
 }
 
+// The same test for a vertex that no |d| > L wrap can reach, on an edge held in registers: the straddle condition by direct
+// comparison (x - y > 0 <=> x > y in IEEE arithmetic with gradual underflow), the crossing only for the edges that straddle.
+__device__ __forceinline__ bool edge_toggles_plain(float2 p, float2 vi, float2 vj) {
+  if ((p.y > vi.y) == (p.y > vj.y)) return false;
+  const float dix = p.x - vi.x, diy = p.y - vi.y, djx = p.x - vj.x, djy = p.y - vj.y;
+  const float num = __fmul_rn(__fsub_rn(djx, dix), __fsub_rn(0.0f, diy)), den = __fsub_rn(djy, diy);
+  const float qa = num * __frcp_rn(den);
+  const float sa = qa + dix;
+  if (fabsf(sa) > 1e-5f * (fabsf(qa) + fabsf(dix))) return 0.0f < sa;
+  return 0.0f < __fadd_rn(__fdiv_rn(num, den), dix);
+}
+
 // One warp per cell.  Shape forces are per-lane ring stencils; the two contact terms are evaluated WARP-COOPERATIVELY:
 // for every (vertex, candidate cell) pair that survives the exact culls, the 32 lanes split the candidate's ring —
 // edges of the even-odd test (parity of the ballots) and vertices of the attraction sum (nonzero terms folded in
@@ -215,6 +227,10 @@ __global__ void __launch_bounds__(T2D, 7) dpm2d_step_kernel(Step2DParams P) {
       const bool wrapPossible = P.pbc && (fmaxf(fabsf(bi0.x - bj1.x), fabsf(bi1.x - bj0.x)) > halfL || fmaxf(fabsf(bi0.y - bj1.y), fabsf(bi1.y - bj0.y)) > halfL);
       int nj = 0, nnear = 0;
       bool staged = false, nearBuilt = false;
+      // the candidate's edges i = lane and i = lane + 32 (rings of up to 64 vertices), loaded once per candidate when the first
+      // vertex asks for the even-odd test: no shared-memory gathers or address arithmetic per tested vertex
+      bool edgesLoaded = false, va = false, vb = false;
+      float2 ea_i = make_float2(0.f, 0.f), ea_j = ea_i, eb_i = ea_i, eb_j = ea_i;
       for (int ch = 0; ch < nchunk; ch++) {
         const int vi = lane + 32 * ch;
         const bool act = vi < n;
@@ -307,11 +323,22 @@ __global__ void __launch_bounds__(T2D, 7) dpm2d_step_kernel(Step2DParams P) {
           const float2 pp = make_float2(__shfl_sync(0xffffffffu, p.x, src), __shfl_sync(0xffffffffu, p.y, src));
           const bool ufar = (mFar >> src) & 1u;
           unsigned par = 0;
-          for (int base = 0; base < nj; base += 32) {
-            const int i = base + lane;
-            bool tg = false;
-            if (i < nj) tg = edge_toggles(pp, sN[i], sN[i == 0 ? nj - 1 : i - 1], ufar, P.L);
-            par ^= __popc(__ballot_sync(0xffffffffu, tg));
+          if (!ufar && nj <= 64) {
+            if (!edgesLoaded) {
+              va = lane < nj; vb = lane + 32 < nj;
+              ea_i = sN[va ? lane : 0]; ea_j = sN[va ? (lane == 0 ? nj - 1 : lane - 1) : 0];
+              eb_i = sN[vb ? lane + 32 : 0]; eb_j = sN[vb ? lane + 31 : 0];
+              edgesLoaded = true;
+            }
+            const bool tga = va && edge_toggles_plain(pp, ea_i, ea_j), tgb = vb && edge_toggles_plain(pp, eb_i, eb_j);
+            par = __popc(__ballot_sync(0xffffffffu, tga)) ^ __popc(__ballot_sync(0xffffffffu, tgb));
+          } else {
+            for (int base = 0; base < nj; base += 32) {
+              const int i = base + lane;
+              bool tg = false;
+              if (i < nj) tg = edge_toggles(pp, sN[i], sN[i == 0 ? nj - 1 : i - 1], ufar, P.L);
+              par ^= __popc(__ballot_sync(0xffffffffu, tg));
+            }
           }
           if (lane == 0) sFound[src + 32 * ch] = (unsigned char)(par & 1u);
           evals++;
