@@ -36,6 +36,7 @@
 // of a neighbour (it needs that neighbour's ghosts of the previous timestep), so a buffer is never overwritten before it
 // has been consumed.  All waits are bounded (a peer that died turns into error 3 instead of a hung GPU).
 // DPM_HALO_NCCL=1 selects the round-1 path (ncclAllGather + ncclSend/ncclRecv of capacity-sized messages).
+#include <cooperative_groups.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -45,6 +46,8 @@
 #include <vector>
 
 #include "dpm3d_ctx.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace dpm {
 
@@ -194,13 +197,19 @@ __device__ __forceinline__ bool reaches(float lo, float hi, float m, float qlo, 
   return fabsf(d) <= 0.5f * (hi - lo) + m + 0.5f * (qhi - qlo);
 }
 
-// ---- 3. send lists (single CTA, deterministic ascending order) ---------------------------------------------------
-__global__ void shard_select_kernel(const float4 *bnd, int n_own, NbrState *st, ShardDev *sd, const float *all, int rank,
-                                    int nranks, int npeers, int peer0, int peer1, int *list0, int *list1, int cap,
-                                    float skin_rel, int pbc, float L) {
-  __shared__ int s_cnt[8][2];
-  __shared__ int s_base[2];
-  __shared__ int s_any;
+// ---- 3. send lists (one cluster of 8 CTAs, deterministic ascending order) -----------------------------------------
+// Round 1 walked the owned cells with a single 256-thread CTA (three barriers and a serial scan per 256 cells: 190 us at
+// 32,768 owned cells).  Now every warp of one 8-CTA cluster owns a contiguous segment of cells: pass 1 counts the wanted
+// cells per peer, the 256 per-warp counts are exchanged through distributed shared memory, and pass 2 scatters at the
+// exclusive offsets — the lists come out in the same ascending order as before.
+constexpr int SEL_CLUSTER = 8, SEL_THREADS = 1024, SEL_WARPS = SEL_THREADS / 32, SEL_GW = SEL_CLUSTER * SEL_WARPS;
+
+__global__ void __launch_bounds__(SEL_THREADS) shard_select_kernel(const float4 *bnd, int n_own, NbrState *st, ShardDev *sd, const float *all,
+                                                                   int rank, int nranks, int npeers, int peer0, int peer1, int *list0,
+                                                                   int *list1, int cap, float skin_rel, int pbc, float L) {
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ int s_cnt[SEL_WARPS][2];  // this CTA's per-warp counts (the other CTAs read them through DSMEM)
+  __shared__ int s_all[SEL_GW][2];     // every warp's counts
   bool any = false;
   float ext = 0.f, pad = 0.f;
   for (int r = 0; r < nranks; r++) {
@@ -208,42 +217,75 @@ __global__ void shard_select_kernel(const float4 *bnd, int n_own, NbrState *st, 
     ext = fmaxf(ext, all[r * GATHER + 3]);
     pad = fmaxf(pad, all[r * GATHER + 4]);
   }
-  if (!any) return;  // uniform
+  if (!any) return;  // uniform over the cluster
   // lists stay valid while every cell stays in its build box (skin/2 each) and pads stay below the build range
   const float margin = skin_rel * ext + RANGE_HEADROOM * pad + 1e-4f * ext;
-  if (threadIdx.x == 0) { st->rebuild = 1; sd->margin = margin; sd->rebuilds_global += 1; s_base[0] = s_base[1] = 0; s_any = 0; }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int crank = (int)cluster.block_rank();
+  if (crank == 0 && threadIdx.x == 0) { st->rebuild = 1; sd->margin = margin; sd->rebuilds_global += 1; }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gw = crank * SEL_WARPS + w;
+  const int seg = ((n_own + SEL_GW - 1) / SEL_GW + 31) & ~31;  // cells per warp
+  const int c_begin = min(n_own, gw * seg), c_end = min(n_own, c_begin + seg);
   const int peers[2] = {peer0, peer1};
-  for (int c0 = 0; c0 < n_own; c0 += blockDim.x) {
-    const int c = c0 + threadIdx.x;
+  float qlo[2] = {0.f, 0.f}, qhi[2] = {0.f, 0.f};
+#pragma unroll
+  for (int p = 0; p < 2; p++)
+    if (p < npeers) { qlo[p] = all[peers[p] * GATHER + 1]; qhi[p] = all[peers[p] * GATHER + 2]; }
+  // pass 1: count
+  int cnt[2] = {0, 0};
+  bool far = false;
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    const int c = c0 + lane;
     bool want[2] = {false, false};
-    if (c < n_own) {
+    if (c < c_end) {
       const float4 lo = bnd[BND * (size_t)c], hi = bnd[BND * (size_t)c + 1];
-      for (int p = 0; p < npeers; p++) want[p] = reaches(lo.x, hi.x, margin, all[peers[p] * GATHER + 1], all[peers[p] * GATHER + 2], pbc, L);
+#pragma unroll
+      for (int p = 0; p < 2; p++) want[p] = p < npeers && reaches(lo.x, hi.x, margin, qlo[p], qhi[p], pbc, L);
       // a cell that reaches a slab which is not an adjacent one cannot be served by this ring exchange
       for (int r = 0; r < nranks; r++)
-        if (r != rank && r != peer0 && r != peer1 && reaches(lo.x, hi.x, margin, all[r * GATHER + 1], all[r * GATHER + 2], pbc, L)) s_any = 1;
+        if (r != rank && r != peer0 && r != peer1 && reaches(lo.x, hi.x, margin, all[r * GATHER + 1], all[r * GATHER + 2], pbc, L)) far = true;
     }
-    unsigned b[2];
-    for (int p = 0; p < 2; p++) { b[p] = __ballot_sync(0xffffffffu, want[p]); if (lane == 0) s_cnt[w][p] = __popc(b[p]); }
-    __syncthreads();
-    for (int p = 0; p < npeers; p++) {
-      int off = s_base[p];
-      for (int i = 0; i < w; i++) off += s_cnt[i][p];
+#pragma unroll
+    for (int p = 0; p < 2; p++) cnt[p] += __popc(__ballot_sync(0xffffffffu, want[p]));
+  }
+  if (far) atomicMax(&sd->error, 2);
+  if (lane == 0) { s_cnt[w][0] = cnt[0]; s_cnt[w][1] = cnt[1]; }
+  cluster.sync();
+  if (threadIdx.x < SEL_GW) {
+    const int *remote = cluster.map_shared_rank(&s_cnt[0][0], threadIdx.x / SEL_WARPS);
+    s_all[threadIdx.x][0] = remote[2 * (threadIdx.x % SEL_WARPS)];
+    s_all[threadIdx.x][1] = remote[2 * (threadIdx.x % SEL_WARPS) + 1];
+  }
+  cluster.sync();  // also keeps every CTA's s_cnt alive until it has been read
+  int off[2] = {0, 0};
+  for (int i = lane; i < gw; i += 32) { off[0] += s_all[i][0]; off[1] += s_all[i][1]; }
+#pragma unroll
+  for (int p = 0; p < 2; p++)
+    for (int o = 16; o > 0; o >>= 1) off[p] += __shfl_xor_sync(0xffffffffu, off[p], o);
+  if (gw == SEL_GW - 1 && lane == 0)
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      const int tot = off[p] + cnt[p];
+      sd->send_count[p] = min(tot, cap);
+      if (tot > cap) atomicMax(&sd->error, 1);
+    }
+  // pass 2: scatter
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    const int c = c0 + lane;
+    bool want[2] = {false, false};
+    if (c < c_end) {
+      const float4 lo = bnd[BND * (size_t)c], hi = bnd[BND * (size_t)c + 1];
+#pragma unroll
+      for (int p = 0; p < 2; p++) want[p] = p < npeers && reaches(lo.x, hi.x, margin, qlo[p], qhi[p], pbc, L);
+    }
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      const unsigned b = __ballot_sync(0xffffffffu, want[p]);
       if (want[p]) {
-        const int pos = off + __popc(b[p] & ((1u << lane) - 1u));
+        const int pos = off[p] + __popc(b & ((1u << lane) - 1u));
         if (pos < cap) (p == 0 ? list0 : list1)[pos] = c;
       }
+      off[p] += __popc(b);
     }
-    __syncthreads();
-    if (threadIdx.x == 0)
-      for (int p = 0; p < 2; p++) { int t = 0; for (int i = 0; i < nw; i++) t += s_cnt[i][p]; s_base[p] += t; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    for (int p = 0; p < 2; p++) { sd->send_count[p] = min(s_base[p], cap); if (s_base[p] > cap) sd->error = 1; }
-    if (s_any) sd->error = 2;
   }
 }
 
@@ -370,10 +412,15 @@ int shard_exchange(dpm3d_ctx *h, int pbc, float L) {
   Nccl &N = nccl();
   ncclComm_t comm = static_cast<ncclComm_t>(h->comm);
   float4 *pos = h->pos[h->cur], *bnd = h->bnd[h->cur];
-  // DPM_TRACE: device time of each phase of ONE exchange (the 150th of the process), events on the stream
+  // DPM_TRACE: device time of each phase of an exchange, events on the stream: the 150th exchange of the process (a step that
+  // keeps its lists) and the first three exchanges after it that rebuild the send lists (found by reading the device counter back,
+  // which synchronises — tracing perturbs those calls, nothing else)
   static const bool trace = getenv("DPM_TRACE") != nullptr;
-  static int ncall = 0;
-  const bool tr = trace && ++ncall == 150;
+  static int ncall = 0, nrebuild_traced = 0;
+  if (trace) ++ncall;
+  const bool tr = trace && (ncall == 150 || (ncall > 150 && nrebuild_traced < 3));
+  int rebuilds_before = 0;
+  if (tr) cudaMemcpyAsync(&rebuilds_before, &h->sd->rebuilds_global, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
   cudaEvent_t tev[7] = {};
   auto mark = [&](int i) { if (tr) { cudaEventCreate(&tev[i]); cudaEventRecord(tev[i], h->stream); } };
   mark(0);
@@ -390,9 +437,17 @@ int shard_exchange(dpm3d_ctx *h, int pbc, float L) {
     DPM_NCCL_TRY(N.AllGather(h->gather_send, h->gather_all, GATHER, ncclFloat, comm, h->stream));
   }
   mark(2);
-  shard_select_kernel<<<1, 256, 0, h->stream>>>(bnd, h->nc, h->st, h->sd, h->gather_all, h->rank, h->nranks, h->npeers, h->peer[0],
-                                                 h->npeers > 1 ? h->peer[1] : -1, h->sendlist[0], h->sendlist[1], h->ghost_cap,
-                                                 h->skin_rel, pbc, L);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(SEL_CLUSTER); cfg.blockDim = dim3(SEL_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = SEL_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DPM_CUDA_TRY(cudaLaunchKernelEx(&cfg, shard_select_kernel, (const float4 *)bnd, h->nc, h->st, h->sd, (const float *)h->gather_all, h->rank,
+                                    h->nranks, h->npeers, h->peer[0], h->npeers > 1 ? h->peer[1] : -1, h->sendlist[0], h->sendlist[1],
+                                    h->ghost_cap, h->skin_rel, pbc, L));
+  }
   mark(3);
   if (h->halo_p2p) {
     // my peer p sees me on its other side (with two ranks the single peer is both neighbours: side 0)
@@ -432,10 +487,16 @@ int shard_exchange(dpm3d_ctx *h, int pbc, float L) {
   mark(6);
   if (tr) {
     cudaEventSynchronize(tev[6]);
+    int rebuilds_after = 0;
+    cudaMemcpy(&rebuilds_after, &h->sd->rebuilds_global, sizeof(int), cudaMemcpyDeviceToHost);
+    const bool rebuilt = rebuilds_after != rebuilds_before;
+    if (rebuilt && ncall != 150) nrebuild_traced++;
     float t[6];
     for (int i = 0; i < 6; i++) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
-    fprintf(stderr, "[dpm3d] rank %d halo exchange, %s (us): prepare %.1f  allgather|mailbox %.1f  select %.1f  pack|push %.1f  send/recv %.1f  unpack %.1f  total %.1f\n",
-            h->rank, h->halo_p2p ? "peer-memory path" : "NCCL path", t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f, t[4] * 1e3f, t[5] * 1e3f, (t[0] + t[1] + t[2] + t[3] + t[4] + t[5]) * 1e3f);
+    if (ncall == 150 || rebuilt)
+      fprintf(stderr, "[dpm3d] rank %d halo exchange %d%s, %s (us): prepare %.1f  allgather|mailbox %.1f  select %.1f  pack|push %.1f  send/recv %.1f  unpack %.1f  total %.1f\n",
+              h->rank, ncall, rebuilt ? " (rebuilds the send lists)" : "", h->halo_p2p ? "peer-memory path" : "NCCL path", t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f,
+              t[3] * 1e3f, t[4] * 1e3f, t[5] * 1e3f, (t[0] + t[1] + t[2] + t[3] + t[4] + t[5]) * 1e3f);
     for (auto &e : tev) cudaEventDestroy(e);
   }
   h->stats.launches += h->halo_p2p ? 5 : 4;
