@@ -684,6 +684,11 @@ int dpm3d_step(dpm3d_t *h, int nsteps, float dt, float Kre, float Kat, int pbc, 
                            : launch_pdl(dpm3d_contact_kernel<false>, h->contact_grid, CONTACT_THREADS, 0, h->stream, p));
     } else if (tr) cudaEventRecord(tev[2], h->stream);
     if (tr) cudaEventRecord(tev[3], h->stream);
+    p.push_slot = nullptr;
+    if (h->nranks > 1 && shard_fused_targets(h, p.push_pos, p.push_bnd, p.push_gidp)) {
+      p.push_slot = reinterpret_cast<const int2 *>(h->push_slot);
+      p.push_gid = h->gid;
+    }
     DPM_CUDA_TRY(launch_step(h, p));
     if (tr) cudaEventRecord(tev[4], h->stream);
     h->cur ^= 1;

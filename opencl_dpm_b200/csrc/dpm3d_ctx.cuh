@@ -84,6 +84,10 @@ struct dpm3d_ctx {
   size_t inbox_bytes = 0;
   int halo_epoch = 0;
   bool halo_p2p = false;
+  // fused push: the step kernel's epilogue stores the cells on the send lists straight into the neighbours' inboxes
+  int *push_slot = nullptr;  // [owned cell][2] slot in the message to peer 0 / 1, or -1 (written with the send lists)
+  int pushed_epoch = -1;     // exchange epoch whose inbox buffers the last step kernel has filled (-1: none)
+  bool halo_fused = false;
 };
 
 namespace dpm {
@@ -92,6 +96,8 @@ int shard_exchange(dpm3d_ctx *h, int pbc, float L);
 int shard_check(dpm3d_ctx *h);   // after a sync: sharding errors (ghost overflow, slabs too thin)
 void shard_free(dpm3d_ctx *h);
 void shard_reset_counters(dpm3d_ctx *h);  // per-upload statistics
+// peer-memory targets of the step kernel about to be launched (the inbox buffers of the NEXT exchange); false: no fused push
+bool shard_fused_targets(dpm3d_ctx *h, float4 *pos[2], float4 *bnd[2], int *gid[2]);
 }  // namespace dpm
 
 

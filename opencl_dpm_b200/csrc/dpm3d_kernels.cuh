@@ -76,6 +76,13 @@ struct Step3DParams {
   float4 *__restrict__ patch_box;  // [cell slot][npatch][2]: (lo.xyz, 0) (hi.xyz, 0)
   int npatch;
   const int *__restrict__ n_total_dev;  // sharded runs: owned + ghost cells present (device-side count); else nullptr
+  // sharded runs, peer-memory halo: a cell on a send list is stored by the step kernel's epilogue straight into the neighbouring
+  // rank's inbox over NVLink (positions by a second bulk store out of shared memory, bounds and global id by the chain warp),
+  // so the exchange in front of the next timestep only has to release the arrival flags (dpm_halo.cu)
+  const int2 *__restrict__ push_slot;  // [owned cell] slot in the message to peer 0 / peer 1, or -1; nullptr: no fused push
+  const int *__restrict__ push_gid;    // [owned cell] global ids
+  float4 *push_pos[2], *push_bnd[2];   // position / bounds areas of the peers' inbox buffers of the NEXT exchange
+  int *push_gidp[2];
   int nc;  // cells stepped by this launch (owned)
   int nv, nf;
   float dt, Kc;
@@ -1187,12 +1194,15 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
   const float4 *gP = P.pos_in + (size_t)ci * nv;
 
   // ---- stage the vertex ring and the per-vertex flags of the current positions (computed by the previous epilogue) ----
+  __shared__ int2 sPush;  // sharded runs: this cell's slots in the neighbouring ranks' inboxes (thread 0's own scratch: read back by thread 0 only)
+  int2 ps0 = make_int2(-1, -1);
   if (tid == 0) {
     mbar_init(&sBar, 1);
     const unsigned pb = (unsigned)(sizeof(float4) * nv);
     mbar_expect_tx(&sBar, pb + (unsigned)nvp);
     bulk_g2s(sP, gP, pb, &sBar);
     bulk_g2s(sVin, P.flag_in + (size_t)ci * nvp, (unsigned)nvp, &sBar);
+    if (P.push_slot) ps0 = P.push_slot[ci];  // requested now, parked in shared memory once the staging wait below is over
   }
   for (int v = tid; v < nvp / 4; v += STEP_THREADS) reinterpret_cast<unsigned *>(sVout)[v] = 0u;
   const float4 cA = P.cellA[ci], cB = P.cellB[ci];
@@ -1211,6 +1221,7 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
   const bool doRep = (P.mask & DPM3D_REPEL) && P.Kc != 0.0f;
   __syncthreads();  // the barrier is initialised
   mbar_wait(&sBar, 0);
+  if (tid == 0) sPush = ps0;
 
   // ---- ring pass: every vertex gathers over its constant ring adjacency ---------------------------------
   DPM_UNROLL(DPM_RING_UNROLL)
@@ -1339,7 +1350,14 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
   }
   fence_async_smem();  // this thread's sP writes -> visible to the bulk store issued below
   __syncthreads();
-  if (tid == 0) bulk_s2g(P.pos_out + (size_t)ci * nv, sP, (unsigned)(sizeof(float4) * nv));
+  if (tid == 0) {
+    bulk_s2g(P.pos_out + (size_t)ci * nv, sP, (unsigned)(sizeof(float4) * nv));
+    if (P.push_slot) {  // sharded: a boundary cell also goes straight into the neighbouring ranks' inboxes (peer memory)
+      const int2 ps = sPush;
+      if (ps.x >= 0) bulk_s2g(P.push_pos[0] + (size_t)ps.x * nv, sP, (unsigned)(sizeof(float4) * nv));
+      if (ps.y >= 0) bulk_s2g(P.push_pos[1] + (size_t)ps.y * nv, sP, (unsigned)(sizeof(float4) * nv));
+    }
+  }
   griddep_launch();  // the next timestep's rebuild kernel may be scheduled; it waits for this grid's completion before it reads anything
 
   // ---- next step's per-cell scalars from the NEW positions --------------------------------------------------
@@ -1385,6 +1403,9 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
     bulk_s2g(P.flag_out + (size_t)ci * nvp, sVout, (unsigned)nvp);
     bulk_wait_all();   // the new positions and vertex flags have left shared memory and landed
     asm volatile("fence.proxy.async;" ::: "memory");  // async-proxy writes (the bulk store) ordered before the release below
+    // (the bulk stores into peer memory, if this cell had any, have completed too.  No system-scope fence here: measured, a
+    // fence.sys by 1.5 % of the CTAs slowed the whole kernel by 2 %; the stores are ordered before the arrival flag by the end
+    // of this grid and the fence.sys of the push kernel's flag thread, three launches later on the same stream)
     __threadfence();
     // publish this cell; the CTA that completes its group evaluates the group's serial chains and assembles its bounds
     const int grp0 = ci / CHAIN_GROUP;
@@ -1407,6 +1428,8 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
     const bool live = cell < gcount;
     const int c0 = grp * CHAIN_GROUP;
     const int tstride = terms_stride(nf);
+    int2 psc = make_int2(-1, -1);  // fused push: the inbox slots of the lane's cell, requested ahead of the chain loop
+    if (P.push_slot && live && chain == 0) psc = P.push_slot[c0 + cell];
     const int niter = max(nv, (nf + 1) >> 1), nchunk = (niter + CHAIN_CH - 1) / CHAIN_CH;
     const int cnt = !live ? 0 : (chain == 3 ? ((nf + 1) >> 1) : nv);
     const unsigned sbase = smem_addr(smem_raw);
@@ -1537,6 +1560,22 @@ __global__ void __launch_bounds__(STEP_THREADS, DPM_STEP_MINB) dpm3d_step_kernel
       // previous volume (compat mode only); l0 travels with the bounds (ghost cells have no parameters)
       bnd_cell[3] = make_float4(0.f, st ? 1.f : 0.f, old2.w, P.cellB[cc].y);
       bnd_cell[4] = make_float4(old2.x, old2.y, old2.z, 0.f);  // kernel point of the new positions
+      if (P.push_slot) {  // the same record (and the cell's global id) into the inboxes of the ranks that have it as a ghost
+        const int2 ps = psc;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const int slot = q == 0 ? ps.x : ps.y;
+          if (slot >= 0) {
+            float4 *pb = P.push_bnd[q] + BND * (size_t)slot;
+            pb[0] = make_float4(l[0], l[1], l[2], rr);
+            pb[1] = make_float4(h[0], h[1], h[2], pad);
+            pb[2] = make_float4(cx, cy, cz, vol);
+            pb[3] = make_float4(0.f, st ? 1.f : 0.f, old2.w, P.cellB[cc].y);
+            pb[4] = make_float4(old2.x, old2.y, old2.z, 0.f);
+            P.push_gidp[q][slot] = P.push_gid[cc];
+          }
+        }
+      }
       {  // neighbour-list validity
         const float4 bl = P.bbox_lo[cc], bh = P.bbox_hi[cc];
         if (l[0] < bl.x || l[1] < bl.y || l[2] < bl.z || h[0] > bh.x || h[1] > bh.y || h[2] > bh.z) P.st->rebuild = 1;

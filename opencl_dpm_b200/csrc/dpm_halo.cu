@@ -64,6 +64,7 @@ struct ShardDev {
   float margin;
   unsigned push_ticket[2];  // CTAs of the push kernel that have stored their cell (per peer; self-resetting)
   unsigned long long sent_bytes;
+  int lists_dirty;  // the send lists were rebuilt in this exchange (select -> push; cleared by the unpack)
 };
 
 // One rank's inbox (peer-mapped by its neighbours).  msg[parity][side]: message from the neighbour on that side;
@@ -206,7 +207,7 @@ constexpr int SEL_CLUSTER = 8, SEL_THREADS = 1024, SEL_WARPS = SEL_THREADS / 32,
 
 __global__ void __launch_bounds__(SEL_THREADS) shard_select_kernel(const float4 *bnd, int n_own, NbrState *st, ShardDev *sd, const float *all,
                                                                    int rank, int nranks, int npeers, int peer0, int peer1, int *list0,
-                                                                   int *list1, int cap, float skin_rel, int pbc, float L) {
+                                                                   int *list1, int cap, float skin_rel, int pbc, float L, int2 *push_slot) {
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ int s_cnt[SEL_WARPS][2];  // this CTA's per-warp counts (the other CTAs read them through DSMEM)
   __shared__ int s_all[SEL_GW][2];     // every warp's counts
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(SEL_THREADS) shard_select_kernel(const float4 
   // lists stay valid while every cell stays in its build box (skin/2 each) and pads stay below the build range
   const float margin = skin_rel * ext + RANGE_HEADROOM * pad + 1e-4f * ext;
   const int crank = (int)cluster.block_rank();
-  if (crank == 0 && threadIdx.x == 0) { st->rebuild = 1; sd->margin = margin; sd->rebuilds_global += 1; }
+  if (crank == 0 && threadIdx.x == 0) { st->rebuild = 1; sd->margin = margin; sd->rebuilds_global += 1; sd->lists_dirty = 1; }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gw = crank * SEL_WARPS + w;
   const int seg = ((n_own + SEL_GW - 1) / SEL_GW + 31) & ~31;  // cells per warp
   const int c_begin = min(n_own, gw * seg), c_end = min(n_own, c_begin + seg);
@@ -277,15 +278,17 @@ __global__ void __launch_bounds__(SEL_THREADS) shard_select_kernel(const float4 
 #pragma unroll
       for (int p = 0; p < 2; p++) want[p] = p < npeers && reaches(lo.x, hi.x, margin, qlo[p], qhi[p], pbc, L);
     }
+    int slot[2] = {-1, -1};
 #pragma unroll
     for (int p = 0; p < 2; p++) {
       const unsigned b = __ballot_sync(0xffffffffu, want[p]);
       if (want[p]) {
         const int pos = off[p] + __popc(b & ((1u << lane) - 1u));
-        if (pos < cap) (p == 0 ? list0 : list1)[pos] = c;
+        if (pos < cap) { (p == 0 ? list0 : list1)[pos] = c; slot[p] = pos; }
       }
       off[p] += __popc(b);
     }
+    if (c < c_end) push_slot[c] = make_int2(slot[0], slot[1]);  // where the step kernel's epilogue stores this cell (fused push)
   }
 }
 
@@ -343,34 +346,50 @@ __global__ void shard_mailbox_kernel(const float *mine, float *all, PeerPtrs pee
   }
 }
 
-// ---- 4'. push: one CTA per (peer, slot) stores its cell straight into the peer's inbox over NVLink ----------------------
+// ---- 4'. push: the listed cells are stored straight into the peer's inbox over NVLink --------------------------------------
+// grid (PUSH_CTAS at most, peers): the CTAs of a peer stride over its slots.  When the step kernel's epilogue has already stored
+// this epoch's cells (fused push, same lists), only the arrival flag is left to release.
+constexpr int PUSH_CTAS = 296;
 __global__ void shard_push_kernel(const float4 *pos, const float4 *bnd, const int *gid, ShardDev *sd, const int *list0, const int *list1,
-                                  unsigned char *dst0, unsigned char *dst1, int *flag0, int *flag1, int cap, int nv, int epoch) {
-  const int p = blockIdx.x / cap, s = blockIdx.x % cap;
+                                  unsigned char *dst0, unsigned char *dst1, int *flag0, int *flag1, int cap, int nv, int epoch, int fused) {
+  const int p = blockIdx.y, G = gridDim.x;
   unsigned char *buf = p == 0 ? dst0 : dst1;
+  int *flag = p == 0 ? flag0 : flag1;
   const int cnt = sd->send_count[p];
-  if (s < cnt) {
+  const unsigned long long bytes = (unsigned long long)cnt * (sizeof(int) + sizeof(float4) * (BND + (size_t)nv)) + 8ull;
+  if (fused && !sd->lists_dirty) {
+    // the stores of the step kernel are complete (that grid has finished); the release orders them before the flag
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      flag[1] = cnt;
+      __threadfence_system();
+      st_release_sys(flag, epoch);
+      atomicAdd(&sd->sent_bytes, bytes);
+    }
+    return;
+  }
+  bool stored = false;
+  for (int s = blockIdx.x; s < cnt; s += G) {
     const int c = (p == 0 ? list0 : list1)[s];
     if (threadIdx.x == 0) reinterpret_cast<int *>(buf + msg_off_gid())[s] = gid[c];
     if (threadIdx.x < BND) reinterpret_cast<float4 *>(buf + msg_off_bnd(cap))[BND * s + threadIdx.x] = bnd[BND * (size_t)c + threadIdx.x];
     float4 *dst = reinterpret_cast<float4 *>(buf + msg_off_pos(cap)) + (size_t)s * nv;
     const float4 *src = pos + (size_t)c * nv;
     for (int v = threadIdx.x; v < nv; v += blockDim.x) dst[v] = src[v];
+    stored = true;
   }
   // the last CTA of this peer to finish releases the arrival flag (count first, epoch last).  One system-scope fence per CTA,
   // by thread 0 behind the CTA barrier (cumulative over the other threads' stores), and none for CTAs that stored nothing.
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (s < cnt) __threadfence_system();
+    if (stored) __threadfence_system();
     const unsigned done = atomicAdd(&sd->push_ticket[p], 1u);
-    if (done == (unsigned)cap - 1u) {
+    if (done == (unsigned)G - 1u) {
       sd->push_ticket[p] = 0u;
       __threadfence_system();
-      int *flag = p == 0 ? flag0 : flag1;
       flag[1] = cnt;
       __threadfence_system();
       st_release_sys(flag, epoch);
-      sd->sent_bytes += (unsigned long long)cnt * (sizeof(int) + sizeof(float4) * (BND + (size_t)nv)) + 8ull;
+      atomicAdd(&sd->sent_bytes, bytes);
     }
   }
 }
@@ -389,18 +408,19 @@ __global__ void shard_unpack_p2p_kernel(float4 *pos, float4 *bnd, int *gid, Shar
     s_cnt[threadIdx.x] = c;
   }
   __syncthreads();
-  const int p = blockIdx.x / cap, s = blockIdx.x % cap;
+  const int p = blockIdx.y, G = gridDim.x;
   const int cnt0 = s_cnt[0], cnt1 = s_cnt[1];
-  if (blockIdx.x == 0 && threadIdx.x == 0) { sd->n_ghost = cnt0 + cnt1; sd->n_total = n_own + cnt0 + cnt1; }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { sd->n_ghost = cnt0 + cnt1; sd->n_total = n_own + cnt0 + cnt1; sd->lists_dirty = 0; }
   const int cnt = p == 0 ? cnt0 : cnt1;
-  if (s >= cnt) return;
   const unsigned char *buf = p == 0 ? buf0 : buf1;
-  const int c = n_own + (p == 0 ? 0 : cnt0) + s;
-  if (threadIdx.x == 0) gid[c] = __ldcg(reinterpret_cast<const int *>(buf + msg_off_gid()) + s);
-  if (threadIdx.x < BND) bnd[BND * (size_t)c + threadIdx.x] = __ldcg(reinterpret_cast<const float4 *>(buf + msg_off_bnd(cap)) + BND * s + threadIdx.x);
-  const float4 *src = reinterpret_cast<const float4 *>(buf + msg_off_pos(cap)) + (size_t)s * nv;
-  float4 *dst = pos + (size_t)c * nv;
-  for (int v = threadIdx.x; v < nv; v += blockDim.x) dst[v] = __ldcg(src + v);
+  for (int s = blockIdx.x; s < cnt; s += G) {
+    const int c = n_own + (p == 0 ? 0 : cnt0) + s;
+    if (threadIdx.x == 0) gid[c] = __ldcg(reinterpret_cast<const int *>(buf + msg_off_gid()) + s);
+    if (threadIdx.x < BND) bnd[BND * (size_t)c + threadIdx.x] = __ldcg(reinterpret_cast<const float4 *>(buf + msg_off_bnd(cap)) + BND * s + threadIdx.x);
+    const float4 *src = reinterpret_cast<const float4 *>(buf + msg_off_pos(cap)) + (size_t)s * nv;
+    float4 *dst = pos + (size_t)c * nv;
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) dst[v] = __ldcg(src + v);
+  }
 }
 
 __global__ void iota_kernel(int *a, int n, int base) {
@@ -446,7 +466,7 @@ int shard_exchange(dpm3d_ctx *h, int pbc, float L) {
     cfg.attrs = attr; cfg.numAttrs = 1;
     DPM_CUDA_TRY(cudaLaunchKernelEx(&cfg, shard_select_kernel, (const float4 *)bnd, h->nc, h->st, h->sd, (const float *)h->gather_all, h->rank,
                                     h->nranks, h->npeers, h->peer[0], h->npeers > 1 ? h->peer[1] : -1, h->sendlist[0], h->sendlist[1],
-                                    h->ghost_cap, h->skin_rel, pbc, L));
+                                    h->ghost_cap, h->skin_rel, pbc, L, reinterpret_cast<int2 *>(h->push_slot)));
   }
   mark(3);
   if (h->halo_p2p) {
@@ -458,13 +478,13 @@ int shard_exchange(dpm3d_ctx *h, int pbc, float L) {
       dst[p] = h->peer_inbox[h->peer[p]] + IL.msg(par, side);
       dflag[p] = reinterpret_cast<int *>(h->peer_inbox[h->peer[p]] + IL.off_flag) + 2 * (par * 2 + side);
     }
-    shard_push_kernel<<<h->ghost_cap * h->npeers, 256, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->sendlist[0], h->sendlist[1], dst[0], dst[1],
-                                                                        dflag[0], dflag[1], h->ghost_cap, h->nv, epoch);
+    shard_push_kernel<<<dim3(h->ghost_cap < PUSH_CTAS ? h->ghost_cap : PUSH_CTAS, h->npeers), 256, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->sendlist[0], h->sendlist[1], dst[0], dst[1],
+                                                                        dflag[0], dflag[1], h->ghost_cap, h->nv, epoch, h->pushed_epoch == epoch ? 1 : 0);
     DPM_CUDA_TRY(cudaGetLastError());
     mark(4);
     mark(5);
     const int *mflag = reinterpret_cast<const int *>(h->inbox + IL.off_flag);
-    shard_unpack_p2p_kernel<<<h->ghost_cap * h->npeers, 128, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->inbox + IL.msg(par, 0), h->inbox + IL.msg(par, 1),
+    shard_unpack_p2p_kernel<<<dim3(h->ghost_cap < PUSH_CTAS ? h->ghost_cap : PUSH_CTAS, h->npeers), 256, 0, h->stream>>>(pos, bnd, h->gid, h->sd, h->inbox + IL.msg(par, 0), h->inbox + IL.msg(par, 1),
                                                                               mflag + 2 * (par * 2 + 0), mflag + 2 * (par * 2 + 1), h->npeers, h->nc,
                                                                               h->ghost_cap, h->nv, epoch);
     DPM_CUDA_TRY(cudaGetLastError());
@@ -517,6 +537,28 @@ int shard_check(dpm3d_ctx *h) {
 
 void shard_reset_counters(dpm3d_ctx *h) {
   if (h->sd) cudaMemsetAsync(&h->sd->sent_bytes, 0, sizeof(unsigned long long), h->stream);
+  h->pushed_epoch = -1;  // new positions were uploaded: whatever a step kernel stored into the peers' inboxes is stale
+}
+
+// The step kernel launched next integrates the state that the NEXT exchange (epoch + 1) sends: hand it the position / bounds /
+// id areas of that exchange's buffers in the neighbours' inboxes.  Safe against overwriting unread data for the same reason as
+// the push kernel: this rank has consumed the neighbour's message of the current epoch, which the neighbour sent after it had
+// consumed everything of the epoch before — the previous user of the buffer with this parity.
+bool shard_fused_targets(dpm3d_ctx *h, float4 *pos[2], float4 *bnd[2], int *gid[2]) {
+  if (!h->halo_p2p || !h->halo_fused || h->halo_epoch <= 0) return false;
+  const int epoch = h->halo_epoch + 1, par = epoch & 1;
+  const InboxLayout IL = inbox_layout(h->msg_bytes, h->nranks);
+  for (int p = 0; p < 2; p++) {
+    pos[p] = nullptr; bnd[p] = nullptr; gid[p] = nullptr;
+    if (p >= h->npeers) continue;
+    const int side = h->npeers == 1 ? 0 : 1 - p;
+    unsigned char *msg = h->peer_inbox[h->peer[p]] + IL.msg(par, side);
+    gid[p] = reinterpret_cast<int *>(msg + msg_off_gid());
+    bnd[p] = reinterpret_cast<float4 *>(msg + msg_off_bnd(h->ghost_cap));
+    pos[p] = reinterpret_cast<float4 *>(msg + msg_off_pos(h->ghost_cap));
+  }
+  h->pushed_epoch = epoch;
+  return true;
 }
 
 void shard_free(dpm3d_ctx *h) {
@@ -527,7 +569,7 @@ void shard_free(dpm3d_ctx *h) {
     h->inbox = nullptr;
   }
   void *ptrs[] = {h->prep_partial, h->prep_ticket, h->gid, h->sd, h->gather_send, h->gather_all, h->sendbuf[0], h->sendbuf[1], h->recvbuf[0], h->recvbuf[1],
-                  h->sendlist[0], h->sendlist[1]};
+                  h->sendlist[0], h->sendlist[1], h->push_slot};
   for (void *p : ptrs) if (p) cudaFree(p);
   h->gid = nullptr; h->sd = nullptr;
   if (h->comm && nccl().CommDestroy) nccl().CommDestroy(static_cast<ncclComm_t>(h->comm));
@@ -600,6 +642,8 @@ int dpm3d_shard_init(dpm3d_t *h, int rank, int nranks, const uint8_t id[128], in
     DPM_CUDA_TRY(cudaMemset(h->recvbuf[p], 0, h->msg_bytes));
     DPM_CUDA_TRY(cudaMalloc(&h->sendlist[p], sizeof(int) * max_ghost));
   }
+  DPM_CUDA_TRY(cudaMalloc(&h->push_slot, sizeof(int) * 2 * (size_t)h->nc));
+  DPM_CUDA_TRY(cudaMemset(h->push_slot, 0xff, sizeof(int) * 2 * (size_t)h->nc));
   DPM_CUDA_TRY(cudaDeviceSynchronize());
   ncclUniqueId u;
   memcpy(&u, id, 128);
@@ -656,6 +700,7 @@ int dpm3d_shard_init(dpm3d_t *h, int rank, int nranks, const uint8_t id[128], in
       for (int r = 0; r < nranks; r++) all_ok = all_ok && fa[(size_t)16 * r] == 1;
     }
     h->halo_p2p = all_ok;
+    h->halo_fused = all_ok && !getenv("DPM_HALO_NO_FUSED");  // DPM_HALO_NO_FUSED=1: the push kernel moves the cells (round-2 first version)
     if (!all_ok && getenv("DPM_TRACE")) fprintf(stderr, "[dpm3d] rank %d: peer-memory halo path unavailable (CUDA IPC), using the NCCL path\n", rank);
   }
   return DPM_OK;

@@ -9,6 +9,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def split_steps(nsteps, calls):
+    base = nsteps // calls
+    return [base + (1 if i < nsteps % calls else 0) for i in range(calls)]
+
+
 def main():
     out, nx, ny, subdiv, nsteps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
     Kat = float(sys.argv[6]) if len(sys.argv) > 6 else 0.0  # != 0: vertex-vertex attraction on (DPM3D_ATTRACT)
@@ -29,9 +34,15 @@ def main():
     h.set_global_ids(d["gid"])
     if Kat != 0.0:
         h.set_force_mask(15 | 16)
+    # calls > 1: the timesteps are split over several step() calls; reupload: the downloaded state is uploaded again between them
+    calls = int(sys.argv[7]) if len(sys.argv) > 7 else 1
+    reupload = bool(int(sys.argv[8])) if len(sys.argv) > 8 else False
     h.upload(d["verts"], *[d[k] for k in PK])
-    h.step(nsteps, float(d["dt"]), float(d["Kre"]), Kat, d["PBC"], float(d["L"]))
-    V, F = h.download()
+    for i, n in enumerate(split_steps(nsteps, calls)):
+        h.step(n, float(d["dt"]), float(d["Kre"]), Kat, d["PBC"], float(d["L"]))
+        V, F = h.download()
+        if reupload and i + 1 < calls:
+            h.upload(V, *[d[k] for k in PK])
     st = h.stats()
     np.savez(os.path.join(out, f"rank{rank}.npz"), gid=d["gid"], verts=V, forces=F, rebuilds=st.rebuilds, halo_bytes=st.halo_bytes,
              contact_evals=st.contact_evals)
