@@ -28,10 +28,14 @@
 //   1. shard_prepare_kernel   as before
 //   2. shard_mailbox_kernel   stores the rank's 8-float summary into every peer's mailbox and waits for theirs (replaces
 //                             the ncclAllGather: one tiny kernel, ~2 NVLink round trips instead of a collective launch)
-//   3. shard_select_kernel    as before, on rebuild only
+//   3. shard_select_kernel    on rebuild only: one 8-CTA cluster builds the send lists (and the per-cell slot table)
 //   4. shard_push_kernel      gathers the listed cells and stores them DIRECTLY into the peer's inbox over NVLink — the
 //                             actual count of cells, not the capacity — then releases an arrival flag (count, epoch)
 //   5. shard_unpack_kernel    acquires the flags of its inbox and appends the ghosts behind the owned cells
+// Fused push (default; DPM_HALO_NO_FUSED=1 turns it off): the send lists also exist as a per-cell slot table, and the STEP kernel's
+// epilogue stores a listed cell's new positions (a second bulk store out of shared memory), bounds and id straight into the
+// neighbour's inbox buffer of the NEXT exchange while the rest of the grid is still integrating.  Step 4 then only releases the
+// arrival flags (unless the lists were rebuilt in this exchange or the state was uploaded since: then it moves the cells itself).
 // Inboxes and mailboxes are double-buffered by the parity of the exchange epoch: a rank can be at most one exchange ahead
 // of a neighbour (it needs that neighbour's ghosts of the previous timestep), so a buffer is never overwritten before it
 // has been consumed.  All waits are bounded (a peer that died turns into error 3 instead of a hung GPU).
