@@ -27,7 +27,8 @@ def _ngpu():
 # step kernel's fused push into the neighbours' inboxes must not survive an upload, and must carry over between calls)
 @pytest.mark.parametrize("world,nx,ny,subdiv,nsteps,Kat,calls,reupload",
                          [(2, 8, 6, 2, 40, 0.0, 1, 0), (2, 6, 4, 3, 12, 0.0, 1, 0), (4, 12, 4, 2, 25, 0.0, 1, 0), (2, 8, 6, 2, 30, 0.5, 1, 0),
-                          (2, 8, 6, 2, 40, 0.0, 3, 0), (2, 8, 6, 2, 40, 0.0, 2, 1), (4, 12, 4, 2, 25, 0.0, 2, 1)])
+                          (2, 8, 6, 2, 40, 0.0, 3, 0), (2, 8, 6, 2, 40, 0.0, 2, 1), (4, 12, 4, 2, 25, 0.0, 2, 1),
+                          (2, 8, 6, 2, 40, 0.0, 2, -1)])  # reupload == -1: the NCCL halo path (DPM_HALO_NCCL=1), two calls
 def test_sharded_run_equals_single_gpu_bit_for_bit(world, nx, ny, subdiv, nsteps, Kat, calls, reupload):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -37,7 +38,12 @@ def test_sharded_run_equals_single_gpu_bit_for_bit(world, nx, ny, subdiv, nsteps
         port = 29500 + (os.getpid() % 2000)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), out, str(nx), str(ny), str(subdiv), str(nsteps), str(Kat), str(calls), str(reupload)]
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        env = dict(os.environ)
+        if reupload < 0:
+            env["DPM_HALO_NCCL"] = "1"
+            reupload = 0
+            cmd[-1] = "0"
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
         d = synth.monolayer3d(nx, ny, subdiv=subdiv)
         PK = ("Kv", "Ka", "Ks", "v0", "a0", "l0")
